@@ -1,0 +1,28 @@
+# Builds the product library (sm_100a only) and the test-only oracle.  No reference sources are
+# compiled here; oracle/Makefile.ref builds the reference's own translation unit into oracle/_ref/.
+NVCC      ?= nvcc
+CSRC      := gpu_matrix_inversion_b200/csrc
+OUT       := gpu_matrix_inversion_b200/libmatinv32.so
+NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O3 \
+             --expt-relaxed-constexpr -Xptxas -v
+CU        := $(wildcard $(CSRC)/*.cu)
+OBJ       := $(CU:.cu=.o) $(CSRC)/mat_inv_32.o
+
+all: $(OUT) oracle
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h include/matinv_shim.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
+
+$(CSRC)/mat_inv_32.o: $(CSRC)/mat_inv_32.cpp include/mat_inv_32.h include/matinv_shim.h
+	g++ -O2 -std=c++17 -fPIC -c $< -o $@
+
+$(OUT): $(OBJ)
+	$(NVCC) -shared -o $@ $(OBJ) -gencode arch=compute_100a,code=sm_100a -lcudart
+
+oracle:
+	gcc -O3 -mfma -mavx2 -ffp-contract=off -fopenmp -fPIC -shared -o oracle/libgj_oracle.so oracle/gj_oracle.c -lm
+
+clean:
+	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log $(OUT) oracle/libgj_oracle.so
+
+.PHONY: all oracle clean

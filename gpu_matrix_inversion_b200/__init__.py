@@ -1,0 +1,250 @@
+"""gpu_matrix_inversion_b200 -- Python host of the B200 Gauss-Jordan inverter.
+
+Thin ctypes binding of the C-ABI in include/matinv_shim.h (libmatinv32.so, built in-tree by
+`make` / __graft_entry__.build()).  The names mirror the reference's two surfaces:
+
+* ``matrix_inv_32(b, N)``   -- the C++ library function (/root/reference/Matlab/mat_inv_32.h:4):
+  row-major flattened input, flattened inverse out, EMPTY result for invalid / singular input.
+* ``driver.matrix_inv(file, N)`` -- the PyOpenCL driver (/root/reference/matrix_inv_pyopencl.py:15-352).
+
+There is no CPU fallback: importing works without a GPU (so the ABI can be inspected), every
+compute call raises / returns the NODEVICE status when no CUDA device is present, and a missing
+extension raises ImportError at import time.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+import numpy as np
+
+__all__ = ["lib", "matrix_inv_32", "invert", "invert_dev", "invert_batched", "invert_batched_dev", "device_count",
+           "last_error", "last_timing", "MatinvError", "OK", "SINGULAR", "FLAG_UNBLOCKED", "FLAG_VERBOSE",
+           "FLAG_NOCHECK", "FLAG_TF32X3", "EXPORTS"]
+
+OK, SINGULAR = 0, 1
+E_INVALID, E_NODEVICE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
+FLAG_TF32X3, FLAG_UNBLOCKED, FLAG_VERBOSE, FLAG_NOCHECK = 1, 2, 4, 8
+
+_SO = Path(__file__).resolve().parent / "libmatinv32.so"
+
+# every symbol include/matinv_shim.h declares (tests check the .so exports each one)
+EXPORTS = [
+    "matinv_device_count", "matinv_last_error", "matinv_shutdown", "matinv_invert_f32", "matinv_invert_f32_dev",
+    "matinv_invert_batched_f32", "matinv_invert_batched_f32_dev", "matinv_shard_panel_bytes", "matinv_shard_create",
+    "matinv_shard_destroy", "matinv_shard_local", "matinv_shard_generate", "matinv_shard_factor",
+    "matinv_shard_apply", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
+    "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
+    "matinv_profile_read",
+]
+
+
+class MatinvError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"matinv error {code}: {text}")
+        self.code = code
+
+
+def _load() -> ctypes.CDLL:
+    if not _SO.exists():
+        raise ImportError(
+            f"{_SO} is missing: build the CUDA extension first (`make` or `python -c 'import __graft_entry__ as g; "
+            f"g.build()'`).  There is no CPU fallback.")
+    L = ctypes.CDLL(str(_SO), mode=ctypes.RTLD_GLOBAL)
+    fp, ip, vp, dp = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)
+    i, ll, ull = ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong
+    L.matinv_device_count.restype = i
+    L.matinv_last_error.restype = ctypes.c_char_p
+    L.matinv_shutdown.restype = None
+    L.matinv_invert_f32.argtypes = [fp, i, fp, ip, i]
+    L.matinv_invert_f32_dev.argtypes = [fp, i, fp, ip, vp, i]
+    L.matinv_invert_batched_f32.argtypes = [fp, i, ll, fp, ip, i]
+    L.matinv_invert_batched_f32_dev.argtypes = [fp, i, ll, fp, ip, vp, i]
+    L.matinv_generate_f32_dev.argtypes = [fp, i, ll, ull, i, i, i, vp]
+    L.matinv_generate_batched_f32_dev.argtypes = [fp, i, ll, ll, ull, vp]
+    L.matinv_residual_f32_dev.argtypes = [fp, fp, i, dp, vp]
+    L.matinv_last_timing.argtypes = [dp, dp]
+    L.matinv_ffma_peak_tflops.argtypes = [dp, vp]
+    L.matinv_profile_enable.argtypes = [i]
+    L.matinv_profile_enable.restype = None
+    L.matinv_profile_read.argtypes = [dp, ctypes.POINTER(ll), dp, ctypes.POINTER(ll)]
+    L.matinv_profile_read.restype = i
+    L.matinv_shard_panel_bytes.argtypes = [i]
+    L.matinv_shard_panel_bytes.restype = ll
+    L.matinv_shard_create.argtypes = [i, i, i, ctypes.POINTER(vp)]
+    L.matinv_shard_destroy.argtypes = [vp]
+    L.matinv_shard_destroy.restype = None
+    L.matinv_shard_local.argtypes = [vp, ctypes.POINTER(ll), ctypes.POINTER(ll)]
+    L.matinv_shard_local.restype = vp
+    L.matinv_shard_generate.argtypes = [vp, ull, i, vp]
+    L.matinv_shard_factor.argtypes = [vp, i, vp, vp]
+    L.matinv_shard_apply.argtypes = [vp, i, vp, vp]
+    L.matinv_shard_status.argtypes = [vp, ip, ip, vp]
+    for name in ("matinv_invert_f32", "matinv_invert_f32_dev", "matinv_invert_batched_f32",
+                 "matinv_invert_batched_f32_dev", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
+                 "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_shard_create",
+                 "matinv_shard_generate", "matinv_shard_factor", "matinv_shard_apply", "matinv_shard_status"):
+        getattr(L, name).restype = i
+    return L
+
+
+lib = _load()
+
+
+def device_count() -> int:
+    return int(lib.matinv_device_count())
+
+
+def last_error() -> str:
+    return lib.matinv_last_error().decode("utf-8", "replace")
+
+
+def last_timing():
+    """(total_s, compute_s) of the last host-pointer inversion on this thread -- the reference's
+    'Tempo Totale Impiegato' / 'Tempo Computazione' (mat_inv_32.cpp:385-386)."""
+    t, c = ctypes.c_double(), ctypes.c_double()
+    if lib.matinv_last_timing(ctypes.byref(t), ctypes.byref(c)) != 0:
+        return None
+    return t.value, c.value
+
+
+def _check(rc: int) -> int:
+    if rc < 0:
+        raise MatinvError(rc, last_error())
+    return rc
+
+
+def invert(A: np.ndarray, flags: int = 0, want_piv: bool = False):
+    """Invert one n x n FP32 matrix held in host memory.  Returns X (or None when singular) and,
+    if want_piv, the pivot vector."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    n = A.shape[0]
+    if A.ndim != 2 or A.shape[1] != n:
+        raise ValueError("square matrix expected")
+    X = np.empty_like(A)
+    piv = np.empty(n, dtype=np.int32) if want_piv else None
+    rc = _check(lib.matinv_invert_f32(A.ctypes.data, n, X.ctypes.data, piv.ctypes.data if want_piv else None, flags))
+    X = X if rc == OK else None
+    return (X, piv) if want_piv else X
+
+
+def matrix_inv_32(matrix_vector, matrix_order: int) -> np.ndarray:
+    """Python twin of `std::vector<float> matrix_inv_32(std::vector<float>, int)`: same checks
+    (mat_inv_32.cpp:207-215, integer-division squareness test included), same error convention
+    (empty result, never raises for bad input / singular matrices / device errors)."""
+    v = np.ascontiguousarray(matrix_vector, dtype=np.float32).ravel()
+    n = int(matrix_order)
+    if n <= 0 or v.size // n != n:
+        return np.empty(0, dtype=np.float32)
+    try:
+        X = invert(v[: n * n].reshape(n, n))
+    except MatinvError:
+        return np.empty(0, dtype=np.float32)
+    return np.empty(0, dtype=np.float32) if X is None else X.ravel()
+
+
+def _torch_ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def invert_dev(A, X=None, piv=None, flags: int = 0):
+    """Device-resident inversion on torch's current stream.  A: (n,n) float32 CUDA tensor (contiguous);
+    X: output tensor (may be A); piv: optional int32 CUDA tensor of n entries.  Returns the status
+    (OK / SINGULAR)."""
+    import torch
+
+    assert A.is_cuda and A.dtype == torch.float32 and A.is_contiguous() and A.dim() == 2 and A.shape[0] == A.shape[1]
+    if X is None:
+        X = torch.empty_like(A)
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    with torch.cuda.device(A.device):
+        rc = lib.matinv_invert_f32_dev(_torch_ptr(A), A.shape[0], _torch_ptr(X),
+                                       _torch_ptr(piv) if piv is not None else None, ctypes.c_void_p(st), flags)
+    _check(rc)
+    return rc, X
+
+
+def invert_batched(A: np.ndarray, flags: int = 0):
+    """Batched small-n inversion from host memory: A (batch, n, n) -> (X, info)."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    b, n, n2 = A.shape
+    assert n == n2
+    X = np.empty_like(A)
+    info = np.empty(b, dtype=np.int32)
+    _check(lib.matinv_invert_batched_f32(A.ctypes.data, n, b, X.ctypes.data, info.ctypes.data, flags))
+    return X, info
+
+
+def invert_batched_dev(A, X=None, info=None, flags: int = 0):
+    """Batched small-n inversion on torch's current stream (asynchronous)."""
+    import torch
+
+    assert A.is_cuda and A.dtype == torch.float32 and A.is_contiguous() and A.dim() == 3 and A.shape[1] == A.shape[2]
+    if X is None:
+        X = torch.empty_like(A)
+    if info is None:
+        info = torch.empty(A.shape[0], dtype=torch.int32, device=A.device)
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    with torch.cuda.device(A.device):
+        _check(lib.matinv_invert_batched_f32_dev(_torch_ptr(A), A.shape[1], A.shape[0], _torch_ptr(X), _torch_ptr(info),
+                                                 ctypes.c_void_p(st), flags))
+    return X, info
+
+
+def generate_dev(n: int, seed: int, kind: str = "uniform", device="cuda"):
+    """Synthetic n x n workload on the device (same bits as oracle.gj_oracle.generate)."""
+    import torch
+
+    A = torch.empty((n, n), dtype=torch.float32, device=device)
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    with torch.cuda.device(A.device):
+        _check(lib.matinv_generate_f32_dev(_torch_ptr(A), n, n, seed, 1 if kind == "diagdom" else 0, 0, n,
+                                           ctypes.c_void_p(st)))
+    return A
+
+
+def generate_batched_dev(n: int, first: int, count: int, seed0: int, device="cuda"):
+    import torch
+
+    A = torch.empty((count, n, n), dtype=torch.float32, device=device)
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    with torch.cuda.device(A.device):
+        _check(lib.matinv_generate_batched_f32_dev(_torch_ptr(A), n, first, count, seed0, ctypes.c_void_p(st)))
+    return A
+
+
+def residual_dev(A, X):
+    """(||A X - I||_F / (n ||A||_F ||X||_F), sqrt(n) - ||A X||_F ~ defect) computed in FP64 on the device."""
+    import math
+
+    import torch
+
+    out = (ctypes.c_double * 3)()
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    with torch.cuda.device(A.device):
+        _check(lib.matinv_residual_f32_dev(_torch_ptr(A), _torch_ptr(X), A.shape[0], out, ctypes.c_void_p(st)))
+    n = A.shape[0]
+    r2, a2, x2 = out[0], out[1], out[2]
+    return math.sqrt(r2) / (n * math.sqrt(a2) * math.sqrt(x2)), r2
+
+
+def ffma_peak_tflops() -> float:
+    import torch
+
+    v = ctypes.c_double()
+    st = torch.cuda.current_stream().cuda_stream
+    _check(lib.matinv_ffma_peak_tflops(ctypes.byref(v), ctypes.c_void_p(st)))
+    return v.value
+
+
+def profile_enable(on: bool = True) -> None:
+    lib.matinv_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """dict(gemm_ms, gemm_launches, gemm_flops, launches) accumulated since profile_enable()."""
+    ms, fl = ctypes.c_double(), ctypes.c_double()
+    gl, al = ctypes.c_longlong(), ctypes.c_longlong()
+    _check(lib.matinv_profile_read(ctypes.byref(ms), ctypes.byref(gl), ctypes.byref(fl), ctypes.byref(al)))
+    return {"gemm_ms": ms.value, "gemm_launches": gl.value, "gemm_flops": fl.value, "launches": al.value}

@@ -1,0 +1,85 @@
+// Load / extract passes around the in-place factorisation.
+//
+//   load_kernel      A (n x n, contiguous) -> W (npad x npad workspace, zero padded).  Takes the place of
+//                    makeAugmentedMatrix (/root/reference/Matlab/mat_inv_32/mat_inv_32/mat_inv_32.cpp:177-192):
+//                    the identity half is never materialised by the in-place form.
+//   colperm_kernel   net effect of the deferred column swaps `for r = n-1..0: swap cols r, piv[r]`
+//                     as a gather list colsrc[j].
+//   extract_kernel   X[i][j] = W[i][colsrc[j]] + isfinite scan.  Takes the place of getInvertedMatrix
+//                    (:195-203) and of the host-side identity check of
+//                    matrix_inv_solution/.../matrix_inversion_FP32.cpp:814-835 (non-finite => {}).
+#include "common.cuh"
+#include "kernels.h"
+
+__global__ void __launch_bounds__(256) load_kernel(const float *__restrict__ A, int n, float *__restrict__ W,
+                                                   long long ld, int npad) {
+    const long long i = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= npad) return;
+    W[i * ld + j] = (i < n && j < n) ? A[i * (long long)n + j] : 0.0f;
+}
+
+// X = M * P_{n-1} ... P_0.  Column j of X is column q(j) of M with q(j) = pi_{n-1}(...pi_0(j)),
+// pi_r the transposition (r, piv[r]).  Once the walker sits on a column < r it can never move again
+// (later transpositions only involve columns >= r), so the loop exits early.
+__global__ void __launch_bounds__(256) colperm_kernel(const int *__restrict__ piv, int n, int *__restrict__ colsrc) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    int c = j;
+    for (int r = 0; r < n; r++) {
+        if (c < r) break;
+        const int p = piv[r];
+        if (c == r) c = p;
+        else if (c == p) c = r;
+    }
+    colsrc[j] = c;
+}
+
+// One CTA per row; the row is staged in shared memory so both the read of W and the write of X are
+// coalesced.  Falls back to a direct gather when the row does not fit (n > 48K).
+__global__ void __launch_bounds__(512) extract_kernel(const float *__restrict__ W, long long ld, int n,
+                                                      const int *__restrict__ colsrc, float *__restrict__ X,
+                                                      int *__restrict__ info, int check, int staged) {
+    extern __shared__ float srow[];
+    const long long i = blockIdx.x;
+    const float *wr = W + i * ld;
+    float *xr = X + i * (long long)n;
+    bool bad = false;
+    if (staged) {
+        for (int j = threadIdx.x; j < n; j += 512) srow[j] = wr[j];
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += 512) {
+            const float v = srow[colsrc[j]];
+            bad |= !isfinite(v);
+            xr[j] = v;
+        }
+    } else {
+        for (int j = threadIdx.x; j < n; j += 512) {
+            const float v = wr[colsrc[j]];
+            bad |= !isfinite(v);
+            xr[j] = v;
+        }
+    }
+    if (check && __syncthreads_or(bad) && threadIdx.x == 0) atomicCAS(info, 0, -1);
+}
+
+void launch_load(const float *A, int n, float *W, long long ld, int npad, cudaStream_t st) {
+    dim3 grid((npad + 255) / 256, npad);
+    load_kernel<<<grid, 256, 0, st>>>(A, n, W, ld, npad);
+}
+
+void launch_colperm_build(const int *piv, int n, int *colsrc, cudaStream_t st) {
+    colperm_kernel<<<(n + 255) / 256, 256, 0, st>>>(piv, n, colsrc);
+}
+
+void launch_extract(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check,
+                    cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    const size_t bytes = (size_t)n * sizeof(float);
+    const int staged = bytes <= 200 * 1024;
+    extract_kernel<<<n, 512, staged ? bytes : 0, st>>>(W, ld, n, colsrc, X, info, check, staged);
+}

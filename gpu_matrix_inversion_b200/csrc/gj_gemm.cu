@@ -1,0 +1,139 @@
+// Trailing update of the blocked Gauss-Jordan:
+//
+//     W[i][j] <- fma(-C[i][kb-1], U[kb-1][j], ... fma(-C[i][1], U[1][j], fma(-C[i][0], U[0][j], W[i][j])))
+//
+// for every row i outside the kb pivot rows and every column j outside the panel.  This is the
+// reference's fixColumnKernel (/root/reference/Matlab/mat_inv_32/mat_inv_32/mat_inv_32.cpp:13-57)
+// applied kb times, with the kb passes over the matrix collapsed into one: a dense FP32
+// contraction with K = kb whose accumulator is SEEDED with the C element and walks k in
+// order -- the exact FMA chain of the unblocked algorithm, hence bit-identical results and
+// bit-identical pivots downstream.  No split-K, no `a - sum`, no tensor-core reordering.
+//
+// FP32 SIMT GEMM, 128x128 CTA tile, 8x8 register tile per thread, K chunks of 16 staged in shared
+// memory by a 3-deep cp.async ring.  Operands are both K-major in HBM (CmT[t][i], U[t][j]) so the
+// staging is a straight copy and the inner loop is 4 LDS.128 + 64 FFMA per k.
+#include "common.cuh"
+#include "kernels.h"
+
+#define GT 128        // tile edge
+#define GBK 16        // k chunk
+#define GSTAGES 3
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct GemmSmem {
+    float a[GSTAGES][GBK][GT];
+    float b[GSTAGES][GBK][GT];
+};
+
+__global__ void __launch_bounds__(256, 2)
+trailing_gemm_kernel(float *__restrict__ W, long long ld, int kt, int kb, const float *__restrict__ CmT,
+                     long long ldc, const float *__restrict__ U, long long ldu) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GemmSmem &s = *reinterpret_cast<GemmSmem *>(smem_raw);
+
+    int tj = blockIdx.x, ti = blockIdx.y;
+    tj += (tj >= kt);  // skip the panel's tile column
+    ti += (ti >= kt);  // skip the pivot rows' tile row
+    const long long i0 = (long long)ti * GT, j0 = (long long)tj * GT;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1, lm = lane >> 3, ln = lane & 7;
+    const int rm = wm * 32 + lm * 4;  // thread rows: rm+{0..3}, rm+16+{0..3}
+    const int cn = wn * 64 + ln * 4;  // thread cols: cn+{0..3}, cn+32+{0..3}
+
+    // ---- operand staging: 16 x 128 floats per operand per chunk = 512 float4, 2 per thread
+    const int lrow = tid >> 5, lcol = (tid & 31) * 4;
+    const float *ga = CmT + i0 + lcol;
+    const float *gb = U + j0 + lcol;
+    const int nchunks = (kb + GBK - 1) / GBK;
+    auto issue = [&](int kc) {
+        const int st = kc % GSTAGES;
+        const long long k = (long long)kc * GBK + lrow;
+        cp_async16(&s.a[st][lrow][lcol], ga + k * ldc);
+        cp_async16(&s.a[st][lrow + 8][lcol], ga + (k + 8) * ldc);
+        cp_async16(&s.b[st][lrow][lcol], gb + k * ldu);
+        cp_async16(&s.b[st][lrow + 8][lcol], gb + (k + 8) * ldu);
+    };
+#pragma unroll
+    for (int kc = 0; kc < GSTAGES - 1; kc++) {
+        if (kc < nchunks) issue(kc);
+        cp_async_commit();
+    }
+
+    // ---- accumulators seeded from C
+    float acc[8][8];
+    float *wp = W + (i0 + rm) * ld + j0 + cn;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float *row = wp + (long long)((i & 3) + (i >> 2) * 16) * ld;
+        const float4 c0 = *reinterpret_cast<const float4 *>(row);
+        const float4 c1 = *reinterpret_cast<const float4 *>(row + 32);
+        acc[i][0] = c0.x; acc[i][1] = c0.y; acc[i][2] = c0.z; acc[i][3] = c0.w;
+        acc[i][4] = c1.x; acc[i][5] = c1.y; acc[i][6] = c1.z; acc[i][7] = c1.w;
+    }
+
+    for (int kc = 0; kc < nchunks; kc++) {
+        cp_async_wait<GSTAGES - 2>();
+        __syncthreads();
+        if (kc + GSTAGES - 1 < nchunks) issue(kc + GSTAGES - 1);
+        cp_async_commit();
+        const int st = kc % GSTAGES;
+        const int kmax = min(GBK, kb - kc * GBK);
+        if (kmax == GBK) {
+#pragma unroll
+            for (int k = 0; k < GBK; k++) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(&s.a[st][k][rm]);
+                const float4 a1 = *reinterpret_cast<const float4 *>(&s.a[st][k][rm + 16]);
+                const float4 b0 = *reinterpret_cast<const float4 *>(&s.b[st][k][cn]);
+                const float4 b1 = *reinterpret_cast<const float4 *>(&s.b[st][k][cn + 32]);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[i][j] = fmaf(-a[i], b[j], acc[i][j]);
+            }
+        } else {
+            for (int k = 0; k < kmax; k++) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(&s.a[st][k][rm]);
+                const float4 a1 = *reinterpret_cast<const float4 *>(&s.a[st][k][rm + 16]);
+                const float4 b0 = *reinterpret_cast<const float4 *>(&s.b[st][k][cn]);
+                const float4 b1 = *reinterpret_cast<const float4 *>(&s.b[st][k][cn + 32]);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[i][j] = fmaf(-a[i], b[j], acc[i][j]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float *row = wp + (long long)((i & 3) + (i >> 2) * 16) * ld;
+        *reinterpret_cast<float4 *>(row) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4 *>(row + 32) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+}
+
+void launch_trailing_gemm(float *W, long long ld, int npad, int k0, int kb, const float *CmT, long long ldc,
+                          const float *U, long long ldu, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(trailing_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
+        configured = true;
+    }
+    const int nt = npad / GT;
+    if (nt <= 1) return;
+    dim3 grid(nt - 1, nt - 1);
+    trailing_gemm_kernel<<<grid, 256, sizeof(GemmSmem), st>>>(W, ld, k0 / GT, kb, CmT, ldc, U, ldu);
+}

@@ -1,0 +1,49 @@
+// Host-side launchers of the sm_100a kernels; every launcher only enqueues on `st`.
+// Reference kernel each one replaces is cited at the definition (csrc/*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+
+// Per-panel bookkeeping living in device memory (written by kernels, never by the host).
+struct PanelState {
+    int pos[2 * 128];      // row index of every slot touched by this panel's swaps (first kb = pivot rows)
+    int content[2 * 128];  // slot whose ORIGINAL data now sits in this slot
+    int m;                 // number of slots in use
+    int pad[3];
+};
+
+// ---- gj_unblocked.cu : north_star kernels (1) and (2) + rank-1 update, one column per launch trio
+void launch_argmax_col(const float *W, long long ld, int n, int col, int row0, u64 *part, int nparts, cudaStream_t st);
+void launch_swap_normalize(float *W, long long ld, int n, int r, const u64 *part, int nparts, float *urow,
+                           float *ccol, int *piv, int *info, cudaStream_t st);
+void launch_rank1_update(float *W, long long ld, int n, int r, const float *urow, const float *ccol, cudaStream_t st);
+
+// ---- gj_panel.cu : panel factorisation (N x kb, kb <= 128)
+void launch_panel_step(const float *in, long long ld_in, float *out, long long ld_out, int n, int kb, int t, int k0,
+                       const u64 *part_in, int nparts, u64 *part_out, float *CmT, long long ldc, int *piv, float *pv,
+                       int *info, PanelState *ps, cudaStream_t st);
+
+// ---- gj_rowblock.cu : row interchanges + row-block recurrence on all non-panel columns
+void launch_rowblock(float *W, long long ld, int ncols_pad, int k0, int kb, const float *CmT, long long ldc,
+                     const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st);
+
+// ---- gj_gemm.cu : trailing update  W[i][j] <- chain_t fma(-CmT[t][i], U[t][j], W[i][j])
+void launch_trailing_gemm(float *W, long long ld, int npad, int k0, int kb, const float *CmT, long long ldc,
+                          const float *U, long long ldu, cudaStream_t st);
+
+// ---- gj_finish.cu : deferred column permutation + extraction + isfinite scan
+void launch_colperm_build(const int *piv, int n, int *colsrc, cudaStream_t st);
+void launch_extract(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check,
+                    cudaStream_t st);
+void launch_load(const float *A, int n, float *W, long long ld, int npad, cudaStream_t st);
+
+// ---- gj_batched.cu : n <= 128, one CTA per matrix
+cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st);
+
+// ---- generate.cu : synthetic workloads, residual, FFMA peak
+void launch_generate(float *A, int n, long long ld, u64 seed, int kind, int col0, int ncols, cudaStream_t st);
+void launch_generate_batched(float *A, int n, long long first, long long count, u64 seed0, cudaStream_t st);
+cudaError_t run_residual(const float *A, const float *X, int n, double *out_host, cudaStream_t st);
+cudaError_t run_ffma_peak(double *tflops, cudaStream_t st);

@@ -1,0 +1,40 @@
+// C++ boundary of the library: the reference's one public function, same signature, same
+// argument checks, same error convention -- implemented on the C-ABI shim instead of OpenCL.
+//
+// Mirrors /root/reference/Matlab/mat_inv_32/mat_inv_32/mat_inv_32.cpp:
+//   :207-209  matrix_order <= 0                      -> {}
+//   :212-215  int(size / matrix_order) != matrix_order -> {}   (integer division: size = N*N + k with
+//             0 <= k < N is accepted and the tail ignored -- replicated on purpose)
+//   :391-394  any device error                        -> {}   (never throws)
+// plus the singular-matrix rule that only the development copy implements
+// (matrix_inv_solution/.../matrix_inversion_FP32.cpp:814-835: left half of [A|I] != I -> {}),
+// which README.md:54 documents as the library contract ("In case of invalid matrix an empty
+// vector is returned").
+#include "../../include/mat_inv_32.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "../../include/matinv_shim.h"
+
+std::vector<float> matrix_inv_32(std::vector<float> matrix_vector, int matrix_order) {
+    if (matrix_order <= 0) return {};
+    const int matrix_height = int(matrix_vector.size() / (size_t)matrix_order);
+    if (matrix_height != matrix_order) return {};
+
+    const size_t count = (size_t)matrix_order * (size_t)matrix_order;
+    std::vector<float> result;
+    try {
+        result.resize(count);
+    } catch (...) {
+        return {};
+    }
+    int flags = 0;
+    const char *verbose = std::getenv("MATINV_VERBOSE");
+    if (verbose && verbose[0] && verbose[0] != '0') flags |= MATINV_FLAG_VERBOSE;
+    const int rc = matinv_invert_f32(matrix_vector.data(), matrix_order, result.data(), nullptr, flags);
+    if (rc == MATINV_OK) return result;
+    if (rc < 0) std::cerr << "ERRORE N\xC2\xB0: " << rc << " (" << matinv_last_error() << ")" << std::endl;  // LIB:392
+    return {};
+}

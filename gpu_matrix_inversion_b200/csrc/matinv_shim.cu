@@ -1,0 +1,413 @@
+// C-ABI shim: context, workspaces and the host-side schedule of the Gauss-Jordan kernels.
+//
+// Replaces everything between the argument checks and the return of the reference's host
+// function (/root/reference/Matlab/mat_inv_32/mat_inv_32/mat_inv_32.cpp, "LIB"):
+//   LIB:239-250  Platform/Device/Context/CommandQueue  -> lazily created process-wide context
+//   LIB:254-263  cl::Buffer x4 (COPY_HOST_PTR)         -> cached device workspaces + cudaMemcpyAsync
+//   LIB:266-290  6 Programs JIT-built at every call    -> sm_100a SASS linked into this library
+//   LIB:293-297  makeAugmentedMatrix                   -> load_kernel (identity never materialised)
+//   LIB:317-362  5 enqueues per column                 -> blocked schedule below
+//   LIB:369-381  getInvertedMatrix + enqueueReadBuffer -> extract_kernel + cudaMemcpyAsync
+// There is no CPU fallback: without a device every compute entry returns MATINV_E_NODEVICE.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <mutex>
+#include <vector>
+
+#include "../../include/matinv_shim.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local double g_t_total = -1.0, g_t_compute = -1.0;
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(MATINV_E_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- profiling (bench.py): launch counter + CUDA events around every trailing GEMM
+struct Profile {
+    bool on = false;
+    long long launches = 0;
+    std::vector<cudaEvent_t> ev;  // pairs
+    size_t used = 0;
+    double gemm_flops = 0.0;
+} g_prof;
+#define COUNT_LAUNCH(k) (g_prof.launches += (k))
+
+cudaEvent_t prof_event() {
+    if (g_prof.used == g_prof.ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        g_prof.ev.push_back(e);
+    }
+    return g_prof.ev[g_prof.used++];
+}
+
+struct Workspace {
+    int npad = 0;
+    float *W = nullptr;     // npad x npad working matrix
+    float *CmT = nullptr;   // 128 x npad multipliers, transposed (row t = step t)
+    float *U = nullptr;     // 128 x npad pivot-row snapshots
+    float *P[2] = {nullptr, nullptr};  // npad x 128 panel ping-pong
+    float *urow = nullptr, *ccol = nullptr, *pv = nullptr;
+    u64 *part[2] = {nullptr, nullptr};
+    int *piv = nullptr, *colsrc = nullptr, *info = nullptr;
+    PanelState *ps = nullptr;
+};
+
+struct Context {
+    std::mutex mu;
+    bool probed = false;
+    int ndev = 0;
+    Workspace ws;
+    cudaStream_t stream = nullptr;
+    float *hostio = nullptr;  // device staging for the host-pointer entries
+    size_t hostio_bytes = 0;
+    int *hostio_i = nullptr;
+    size_t hostio_i_bytes = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+} g;
+
+int probe_locked() {
+    if (!g.probed) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; cudaGetLastError(); }
+        g.ndev = n;
+        g.probed = true;
+    }
+    return g.ndev;
+}
+
+void free_ws(Workspace &w) {
+    cudaFree(w.W); cudaFree(w.CmT); cudaFree(w.U); cudaFree(w.P[0]); cudaFree(w.P[1]);
+    cudaFree(w.urow); cudaFree(w.ccol); cudaFree(w.pv); cudaFree(w.part[0]); cudaFree(w.part[1]);
+    cudaFree(w.piv); cudaFree(w.colsrc); cudaFree(w.info); cudaFree(w.ps);
+    w = Workspace();
+}
+
+int ensure_ws(int npad) {
+    Workspace &w = g.ws;
+    if (w.npad == npad) return 0;
+    free_ws(w);
+    const size_t N = (size_t)npad;
+    CK(cudaMalloc(&w.W, N * N * sizeof(float)));
+    CK(cudaMalloc(&w.CmT, MATINV_NB * N * sizeof(float)));
+    CK(cudaMalloc(&w.U, MATINV_NB * N * sizeof(float)));
+    CK(cudaMalloc(&w.P[0], N * MATINV_NB * sizeof(float)));
+    CK(cudaMalloc(&w.P[1], N * MATINV_NB * sizeof(float)));
+    CK(cudaMalloc(&w.urow, N * sizeof(float)));
+    CK(cudaMalloc(&w.ccol, N * sizeof(float)));
+    CK(cudaMalloc(&w.pv, MATINV_NB * sizeof(float)));
+    const size_t nparts = N / MATINV_RB;
+    CK(cudaMalloc(&w.part[0], nparts * sizeof(u64)));
+    CK(cudaMalloc(&w.part[1], nparts * sizeof(u64)));
+    CK(cudaMalloc(&w.piv, N * sizeof(int)));
+    CK(cudaMalloc(&w.colsrc, N * sizeof(int)));
+    CK(cudaMalloc(&w.info, sizeof(int)));
+    CK(cudaMalloc(&w.ps, sizeof(PanelState)));
+    CK(cudaMemset(w.CmT, 0, MATINV_NB * N * sizeof(float)));
+    CK(cudaMemset(w.U, 0, MATINV_NB * N * sizeof(float)));
+    CK(cudaMemset(w.P[0], 0, N * MATINV_NB * sizeof(float)));
+    CK(cudaMemset(w.P[1], 0, N * MATINV_NB * sizeof(float)));
+    w.npad = npad;
+    return 0;
+}
+
+int ensure_stream() {
+    if (!g.stream) {
+        CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&g.ev[0]));
+        CK(cudaEventCreate(&g.ev[1]));
+    }
+    return 0;
+}
+
+// ---- schedules ------------------------------------------------------------------------------
+
+// Unblocked: three launches per column (north_star kernels 1 and 2 + rank-1 update).
+void schedule_unblocked(Workspace &w, int n, cudaStream_t st) {
+    const long long ld = w.npad;
+    const int nparts = (n + MATINV_RB - 1) / MATINV_RB;
+    for (int r = 0; r < n; r++) {
+        launch_argmax_col(w.W, ld, n, r, r, w.part[0], nparts, st);
+        launch_swap_normalize(w.W, ld, n, r, w.part[0], nparts, w.urow, w.ccol, w.piv, w.info, st);
+        launch_rank1_update(w.W, ld, n, r, w.urow, w.ccol, st);
+        COUNT_LAUNCH(3);
+    }
+}
+
+// Blocked right-looking: per 128-wide panel  factor -> (swaps + recurrence) -> trailing GEMM.
+void schedule_blocked(Workspace &w, int n, cudaStream_t st) {
+    const long long ld = w.npad;
+    const int nparts = (n + MATINV_RB - 1) / MATINV_RB;
+    for (int k0 = 0; k0 < n; k0 += MATINV_NB) {
+        const int kb = (n - k0 < MATINV_NB) ? n - k0 : MATINV_NB;
+        launch_argmax_col(w.W, ld, n, k0, k0, w.part[0], nparts, st);
+        COUNT_LAUNCH(1 + kb);
+        for (int t = 0; t < kb; t++) {
+            const float *in = (t == 0) ? w.W + k0 : w.P[(t - 1) & 1];
+            const long long ld_in = (t == 0) ? ld : MATINV_NB;
+            const bool last = (t == kb - 1) && kb > 1;
+            float *out = last ? w.W + k0 : w.P[t & 1];
+            const long long ld_out = last ? ld : MATINV_NB;
+            launch_panel_step(in, ld_in, out, ld_out, n, kb, t, k0, w.part[t & 1], nparts, w.part[(t + 1) & 1], w.CmT,
+                              ld, w.piv, w.pv, w.info, w.ps, st);
+        }
+        if (kb == 1)  // single-column panel: in == out would alias, so it went through P[0]
+            cudaMemcpy2DAsync(w.W + k0, ld * sizeof(float), w.P[0], MATINV_NB * sizeof(float),
+                              MATINV_NB * sizeof(float), n, cudaMemcpyDeviceToDevice, st);
+        if (w.npad > MATINV_NB) {
+            launch_rowblock(w.W, ld, w.npad, k0, kb, w.CmT, ld, w.pv, w.ps, w.U, ld, st);
+            if (g_prof.on) cudaEventRecord(prof_event(), st);
+            launch_trailing_gemm(w.W, ld, w.npad, k0, kb, w.CmT, ld, w.U, ld, st);
+            if (g_prof.on) {
+                cudaEventRecord(prof_event(), st);
+                const double m = (double)(w.npad - MATINV_NB);
+                g_prof.gemm_flops += 2.0 * m * m * kb;
+            }
+            COUNT_LAUNCH(2);
+        }
+    }
+}
+
+int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cudaStream_t st, int flags) {
+    if (flags & MATINV_FLAG_TF32X3) return fail(MATINV_E_UNSUPPORTED, "3xTF32 trailing update is not built in this round");
+    const int npad = ((n + MATINV_NB - 1) / MATINV_NB) * MATINV_NB;
+    int rc = ensure_ws(npad);
+    if (rc) return rc;
+    Workspace &w = g.ws;
+    CK(cudaMemsetAsync(w.info, 0, sizeof(int), st));
+    launch_load(A_dev, n, w.W, npad, npad, st);
+    if (flags & MATINV_FLAG_UNBLOCKED) schedule_unblocked(w, n, st);
+    else schedule_blocked(w, n, st);
+    COUNT_LAUNCH(3);
+    launch_colperm_build(w.piv, n, w.colsrc, st);
+    launch_extract(w.W, npad, n, w.colsrc, X_dev, w.info, !(flags & MATINV_FLAG_NOCHECK), st);
+    if (piv_dev) CK(cudaMemcpyAsync(piv_dev, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    int info = 0;
+    CK(cudaMemcpyAsync(&info, w.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (info != 0) {
+        if (info > 0) snprintf(g_err, sizeof(g_err), "singular: zero or non-finite pivot at column %d", info - 1);
+        else snprintf(g_err, sizeof(g_err), "singular: non-finite entry in the inverse");
+        return MATINV_SINGULAR;
+    }
+    return MATINV_OK;
+}
+
+int ensure_hostio(size_t bytes, size_t ibytes) {
+    if (g.hostio_bytes < bytes) {
+        cudaFree(g.hostio);
+        g.hostio = nullptr; g.hostio_bytes = 0;
+        CK(cudaMalloc(&g.hostio, bytes));
+        g.hostio_bytes = bytes;
+    }
+    if (g.hostio_i_bytes < ibytes) {
+        cudaFree(g.hostio_i);
+        g.hostio_i = nullptr; g.hostio_i_bytes = 0;
+        CK(cudaMalloc(&g.hostio_i, ibytes));
+        g.hostio_i_bytes = ibytes;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int matinv_device_count(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    return probe_locked();
+}
+
+const char *matinv_last_error(void) { return g_err; }
+
+void matinv_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.probed || g.ndev == 0) return;
+    free_ws(g.ws);
+    cudaFree(g.hostio); g.hostio = nullptr; g.hostio_bytes = 0;
+    cudaFree(g.hostio_i); g.hostio_i = nullptr; g.hostio_i_bytes = 0;
+    if (g.stream) {
+        cudaEventDestroy(g.ev[0]); cudaEventDestroy(g.ev[1]);
+        cudaStreamDestroy(g.stream);
+        g.stream = nullptr;
+    }
+}
+
+int matinv_invert_f32_dev(const float *A_dev, int n, float *X_dev, int *piv_dev, void *stream, int flags) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_dev || !X_dev) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    return invert_dev_locked(A_dev, n, X_dev, piv_dev, (cudaStream_t)stream, flags);
+}
+
+int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, int flags) {
+    g_err[0] = 0;
+    g_t_total = g_t_compute = -1.0;
+    if (n <= 0 || !A_host || !X_host) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = ensure_stream();
+    if (rc) return rc;
+    const size_t bytes = (size_t)n * n * sizeof(float);
+    rc = ensure_hostio(bytes, (size_t)n * sizeof(int));
+    if (rc) return rc;
+    cudaStream_t st = g.stream;
+    CK(cudaMemcpyAsync(g.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(g.ev[0], st));
+    rc = invert_dev_locked(g.hostio, n, g.hostio, piv_host ? g.hostio_i : nullptr, st, flags);
+    if (rc < 0) return rc;
+    CK(cudaEventRecord(g.ev[1], st));
+    if (rc == MATINV_OK) CK(cudaMemcpyAsync(X_host, g.hostio, bytes, cudaMemcpyDeviceToHost, st));
+    if (piv_host) CK(cudaMemcpyAsync(piv_host, g.hostio_i, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+    g_t_compute = ms * 1e-3;
+    g_t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (flags & MATINV_FLAG_VERBOSE) {  // the reference's two stdout lines (LIB:385-386)
+        printf("Tempo Totale Impiegato: %g seconds\n", g_t_total);
+        printf("Tempo Computazione: %g seconds\n", g_t_compute);
+        fflush(stdout);
+    }
+    return rc;
+}
+
+int matinv_invert_batched_f32_dev(const float *A_dev, int n, long long batch, float *X_dev, int *info_dev,
+                                  void *stream, int flags) {
+    (void)flags;
+    g_err[0] = 0;
+    if (n <= 0 || n > 128 || batch < 0 || !A_dev || !X_dev) return fail(MATINV_E_INVALID, "invalid argument (need 1 <= n <= 128)");
+    if (batch == 0) return MATINV_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    CK(launch_batched(A_dev, n, batch, X_dev, info_dev, (cudaStream_t)stream));
+    COUNT_LAUNCH(1);
+    return MATINV_OK;
+}
+
+int matinv_invert_batched_f32(const float *A_host, int n, long long batch, float *X_host, int *info_host,
+                              int flags) {
+    (void)flags;
+    g_err[0] = 0;
+    if (n <= 0 || n > 128 || batch < 0 || !A_host || !X_host) return fail(MATINV_E_INVALID, "invalid argument (need 1 <= n <= 128)");
+    if (batch == 0) return MATINV_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    int rc = ensure_stream();
+    if (rc) return rc;
+    const size_t bytes = (size_t)batch * n * n * sizeof(float);
+    rc = ensure_hostio(bytes, (size_t)batch * sizeof(int));
+    if (rc) return rc;
+    cudaStream_t st = g.stream;
+    CK(cudaMemcpyAsync(g.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
+    CK(launch_batched(g.hostio, n, batch, g.hostio, g.hostio_i, st));
+    COUNT_LAUNCH(1);
+    CK(cudaMemcpyAsync(X_host, g.hostio, bytes, cudaMemcpyDeviceToHost, st));
+    int *info = info_host;
+    int *tmp = nullptr;
+    if (!info) { tmp = (int *)malloc((size_t)batch * sizeof(int)); info = tmp; }
+    CK(cudaMemcpyAsync(info, g.hostio_i, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int any = 0;
+    for (long long b = 0; b < batch; b++) any |= (info[b] != 0);
+    free(tmp);
+    return any ? MATINV_SINGULAR : MATINV_OK;
+}
+
+int matinv_generate_f32_dev(float *A_dev, int n, long long ld, unsigned long long seed, int kind, int col0,
+                            int ncols, void *stream) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_dev || ld < ncols || col0 < 0 || ncols <= 0 || col0 + ncols > n) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    launch_generate(A_dev, n, ld, seed, kind, col0, ncols, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return MATINV_OK;
+}
+
+int matinv_generate_batched_f32_dev(float *A_dev, int n, long long first, long long count,
+                                    unsigned long long seed0, void *stream) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_dev || count <= 0) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    launch_generate_batched(A_dev, n, first, count, seed0, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return MATINV_OK;
+}
+
+int matinv_residual_f32_dev(const float *A_dev, const float *X_dev, int n, double *out_host, void *stream) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_dev || !X_dev || !out_host) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    CK(run_residual(A_dev, X_dev, n, out_host, (cudaStream_t)stream));
+    return MATINV_OK;
+}
+
+int matinv_last_timing(double *total_s, double *compute_s) {
+    if (g_t_total < 0) return 1;
+    if (total_s) *total_s = g_t_total;
+    if (compute_s) *compute_s = g_t_compute;
+    return 0;
+}
+
+void matinv_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    g_prof.on = on != 0;
+    g_prof.launches = 0;
+    g_prof.used = 0;
+    g_prof.gemm_flops = 0.0;
+}
+
+int matinv_profile_read(double *gemm_ms, long long *gemm_launches, double *gemm_flops, long long *all_launches) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+        float t = 0.f;
+        if (cudaEventSynchronize(g_prof.ev[i + 1]) != cudaSuccess) return fail(MATINV_E_CUDA, "profile event sync failed");
+        cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+        ms += t;
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_launches) *gemm_launches = (long long)(g_prof.used / 2);
+    if (gemm_flops) *gemm_flops = g_prof.gemm_flops;
+    if (all_launches) *all_launches = g_prof.launches;
+    return MATINV_OK;
+}
+
+int matinv_ffma_peak_tflops(double *tflops_out, void *stream) {
+    g_err[0] = 0;
+    if (!tflops_out) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    CK(run_ffma_peak(tflops_out, (cudaStream_t)stream));
+    return MATINV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+/*
+ * matinv_shim.h -- C-ABI boundary of the B200 Gauss-Jordan inverter (libmatinv32.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  It replaces the
+ * OpenCL platform / context / program / queue / buffer code of the reference's host function
+ * (/root/reference/Matlab/mat_inv_32/mat_inv_32/mat_inv_32.cpp, abbreviated LIB below) and
+ * is what mat_inv_32.cpp (the C++ `matrix_inv_32`), the Python ctypes host
+ * (gpu_matrix_inversion_b200/) and bench.py bind.  INTEGRATION.md shows the reference-side
+ * binding.
+ *
+ * Conventions (all entry points):
+ *   - matrices are row-major, element (i,j) at i*n + j, FP32       (LIB:183, LIB:201)
+ *   - return 0 = ok, 1 = singular / non-finite (the C++ layer returns {}),
+ *     < 0 = error (MATINV_E_*); matinv_last_error() holds the text (thread-local)
+ *   - never throws, never aborts; no CPU fallback: without a CUDA device every compute entry
+ *     returns MATINV_E_NODEVICE
+ *   - 64-bit indexing internally (the reference overflows `int` at n >= 32768, LIB:232, LIB:70)
+ */
+#ifndef MATINV_SHIM_H
+#define MATINV_SHIM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MATINV_OK 0
+#define MATINV_SINGULAR 1
+#define MATINV_E_INVALID (-1)  /* bad argument                                   */
+#define MATINV_E_NODEVICE (-2) /* no CUDA device (reference: UB at LIB:239-240)  */
+#define MATINV_E_CUDA (-3)     /* CUDA runtime error, text in matinv_last_error  */
+#define MATINV_E_UNSUPPORTED (-4)
+
+/* flags */
+#define MATINV_FLAG_TF32X3 1    /* reserved: 3xTF32 tcgen05 trailing update (not bit-exact)      */
+#define MATINV_FLAG_UNBLOCKED 2 /* force the unblocked 3-kernel-per-column path (parity checks)  */
+#define MATINV_FLAG_VERBOSE 4   /* print the reference's two stdout lines (LIB:385-386)          */
+#define MATINV_FLAG_NOCHECK 8   /* skip the final isfinite scan (kept off the hot path timing)   */
+
+/* Replaces cl::Platform::get / getDevices (LIB:239-244).  Number of usable CUDA devices, 0 if none. */
+int matinv_device_count(void);
+
+/* Text of the last error on this thread ("" if none). */
+const char *matinv_last_error(void);
+
+/* Frees the process-wide context (streams, workspaces).  Replaces buffers.clear() (LIB:388). */
+void matinv_shutdown(void);
+
+/* Whole `matrix_inv_32` body below the argument checks (LIB:219-389): H2D, N Gauss-Jordan steps
+ * with partial pivoting, extraction, D2H.  A_host/X_host: n*n floats (may alias); piv_host:
+ * n ints or NULL, piv[r] = row chosen as pivot at step r (arg max |.| over rows >= r, lowest
+ * index on ties). */
+int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, int flags);
+
+/* Same with device pointers on the current device: the "Tempo Computazione" window (LIB:316-365)
+ * plus extraction (LIB:369-376), no PCIe traffic.  Work is enqueued on `stream` (a cudaStream_t,
+ * NULL = default stream); the call returns after the stream has drained because the status word
+ * is read back.  A_dev and X_dev may alias. */
+int matinv_invert_f32_dev(const float *A_dev, int n, float *X_dev, int *piv_dev, void *stream, int flags);
+
+/* Batched small-n path (n <= 128), one CTA per matrix.  The reference has no batched entry: this
+ * is `for b: matrix_inv_32(A[b], n)` in one launch.  A/X: batch*n*n floats; info: per-matrix
+ * status (0 ok, r+1 zero/non-finite pivot at step r, -1 non-finite inverse) or NULL.
+ * Returns 0 when every matrix inverted, 1 when at least one is singular, < 0 on error. */
+int matinv_invert_batched_f32(const float *A_host, int n, long long batch, float *X_host, int *info_host,
+                              int flags);
+int matinv_invert_batched_f32_dev(const float *A_dev, int n, long long batch, float *X_dev, int *info_dev,
+                                  void *stream, int flags);
+
+/* ---- column-sharded single inversion: per-rank primitives, one process per GPU ---------------
+ * The host (Python + torch.distributed, or any MPI-like launcher) owns the exchange step; these
+ * calls own the math.  Columns are dealt block-cyclically in blocks of 128: global column block J
+ * lives on rank J % world.  See DESIGN.md "multi-GPU". */
+typedef struct matinv_shard matinv_shard_t;
+/* panel message: what the owner of block J broadcasts.  Size in bytes for a given n. */
+long long matinv_shard_panel_bytes(int n);
+int matinv_shard_create(int n, int rank, int world, matinv_shard_t **out);
+void matinv_shard_destroy(matinv_shard_t *s);
+/* local storage: n_pad x local_cols floats, row-major with leading dimension local_ld */
+float *matinv_shard_local(matinv_shard_t *s, long long *local_cols, long long *local_ld);
+/* fill the local columns with the synthetic workload (same bits as the unsharded generator) */
+int matinv_shard_generate(matinv_shard_t *s, unsigned long long seed, int kind, void *stream);
+/* owner only: factor panel J in place and pack the message into panel_dev */
+int matinv_shard_factor(matinv_shard_t *s, int J, void *panel_dev, void *stream);
+/* every rank: apply panel J's swaps + row-block recurrence + trailing update to the local columns */
+int matinv_shard_apply(matinv_shard_t *s, int J, const void *panel_dev, void *stream);
+/* after the last block: deferred column permutation.  Produces, for local column blocks, the list
+ * of source global columns (host array of local_cols ints) -- the host moves columns accordingly. */
+int matinv_shard_status(matinv_shard_t *s, int *info_host, int *piv_host, void *stream);
+
+/* ---- synthetic workloads and checks on the device (bench + tests; same bits as oracle/) ------
+ * kind 0: U[0,100) counter-based; kind 1: diagonally dominant.  Fills A_dev[i*ld + (j-col0)] for
+ * j in [col0, col0+ncols) of the n x n matrix with the given seed. */
+int matinv_generate_f32_dev(float *A_dev, int n, long long ld, unsigned long long seed, int kind, int col0,
+                            int ncols, void *stream);
+/* Batched generator: matrix b (global index first+b) uses seed seed0 + first + b. */
+int matinv_generate_batched_f32_dev(float *A_dev, int n, long long first, long long count,
+                                    unsigned long long seed0, void *stream);
+/* ||A X - I||_F^2, ||A||_F^2, ||X||_F^2 in FP64 on the device (verification GEMM, replaces
+ * SOL/matrix_multiply.cpp:15-212).  out_host[3]. */
+int matinv_residual_f32_dev(const float *A_dev, const float *X_dev, int n, double *out_host, void *stream);
+
+/* Seconds spent by the last matinv_invert_f32 on this thread: total (H2D+compute+D2H, the
+ * reference's "Tempo Totale") and compute ("Tempo Computazione").  Returns 0 if available. */
+int matinv_last_timing(double *total_s, double *compute_s);
+
+/* Profiling hooks for bench.py.  With profiling enabled the shim brackets every trailing-update
+ * (GEMM) launch with CUDA events on the launching stream.  matinv_profile_read returns, for the
+ * calls made since the last matinv_profile_enable: summed GEMM time (ms), number of GEMM launches,
+ * algorithmic flops of those launches, and the number of kernels launched in total. */
+void matinv_profile_enable(int on);
+int matinv_profile_read(double *gemm_ms, long long *gemm_launches, double *gemm_flops, long long *all_launches);
+
+/* FFMA throughput micro-benchmark (TFLOP/s) -- the FP32 SIMT roofline denominator, measured live. */
+int matinv_ffma_peak_tflops(double *tflops_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATINV_SHIM_H */

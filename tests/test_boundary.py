@@ -1,0 +1,83 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, the C++ symbol has the reference's mangled name, and the argument conventions of
+matrix_inv_32 (mat_inv_32.cpp:207-215) hold without a GPU."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    import gpu_matrix_inversion_b200 as m
+
+    header = (ROOT / "include" / "matinv_shim.h").read_text()
+    declared = sorted(set(re.findall(r"\b(matinv_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(ROOT / "gpu_matrix_inversion_b200" / "libmatinv32.so")],
+                         capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (\w+)", out))
+    missing = [d for d in declared if d not in exported]
+    assert not missing, missing
+    assert sorted(m.EXPORTS) == declared
+    # the C++ surface: Itanium mangling of std::vector<float> matrix_inv_32(std::vector<float>, int)
+    assert "_Z13matrix_inv_32St6vectorIfSaIfEEi" in exported
+
+
+def test_python_twin_argument_conventions_without_device():
+    import gpu_matrix_inversion_b200 as m
+
+    assert m.matrix_inv_32(np.ones(4, np.float32), 0).size == 0        # N <= 0
+    assert m.matrix_inv_32(np.ones(4, np.float32), -3).size == 0
+    assert m.matrix_inv_32(np.ones(5, np.float32), 3).size == 0        # int(5/3)=1 != 3
+    assert m.matrix_inv_32(np.ones(12, np.float32), 3).size == 0       # int(12/3)=4 != 3
+    if m.device_count() == 0:
+        # no CPU fallback: a valid request fails loudly at the ABI and yields {} at the library surface
+        assert m.matrix_inv_32(np.eye(2, dtype=np.float32).ravel(), 2).size == 0
+        with pytest.raises(m.MatinvError) as e:
+            m.invert(np.eye(2, dtype=np.float32))
+        assert e.value.code == m.E_NODEVICE
+        with pytest.raises(m.MatinvError):
+            m.invert_batched(np.zeros((1, 4, 4), np.float32))
+
+
+def test_cpp_surface_links_and_follows_conventions(tmp_path):
+    """Compile a caller against include/mat_inv_32.h exactly like a user of the reference header."""
+    src = tmp_path / "caller.cpp"
+    src.write_text(r'''
+#include "mat_inv_32.h"
+#include <cstdio>
+int main() {
+    std::vector<float> a = {4, 7, 2, 6};
+    int bad = 0;
+    bad |= !matrix_inv_32(a, 0).empty();
+    bad |= !matrix_inv_32(a, -1).empty();
+    bad |= !matrix_inv_32(a, 3).empty();               // int(4/3) = 1 != 3
+    std::vector<float> b = {4, 7, 2, 6, 99};           // size = N*N + k, k < N: accepted, tail ignored
+    std::vector<float> r = matrix_inv_32(b, 2);
+    std::vector<float> s = matrix_inv_32(std::vector<float>{1, 2, 2, 4}, 2);   // singular
+    std::printf("%d %zu %zu\n", bad, r.size(), s.size());
+    if (r.size() == 4) std::printf("%.6f %.6f %.6f %.6f\n", r[0], r[1], r[2], r[3]);
+    return bad;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = ROOT / "gpu_matrix_inversion_b200"
+    subprocess.run(["g++", "-std=c++14", "-I", str(ROOT / "include"), str(src), "-o", str(exe), "-L", str(libdir),
+                    "-lmatinv32", f"-Wl,-rpath,{libdir}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"],
+                   check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    first = p.stdout.splitlines()[0].split()
+    assert first[0] == "0"
+    import gpu_matrix_inversion_b200 as m
+
+    if m.device_count() == 0:
+        assert first[1] == "0" and first[2] == "0"          # no device -> {} (never UB like platforms[0])
+    else:
+        assert first[1] == "4" and first[2] == "0"          # inverse returned; singular -> {}
+        vals = [float(x) for x in p.stdout.splitlines()[1].split()]
+        assert np.allclose(vals, [0.6, -0.7, -0.2, 0.4], atol=1e-6)

