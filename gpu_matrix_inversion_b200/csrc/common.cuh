@@ -56,5 +56,10 @@ __host__ __device__ __forceinline__ float gj_u100(u64 seed, u64 idx) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z = z ^ (z >> 31);
+#ifdef __CUDA_ARCH__
+    // explicit rn multiply: keeps nvcc from contracting "* 100.0f" with a following add into an FMA
+    return __fmul_rn(__fmul_rn((float)(z >> 40), 1.0f / 16777216.0f), 100.0f);
+#else
     return (float)(z >> 40) * (1.0f / 16777216.0f) * 100.0f;
+#endif
 }

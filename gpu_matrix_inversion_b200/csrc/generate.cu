@@ -26,8 +26,8 @@ __global__ void __launch_bounds__(128) diagdom_kernel(float *__restrict__ A, int
     if (i >= n || i < col0 || i >= col0 + ncols) return;
     float s = 0.0f;
     for (int j = 0; j < n; j++)
-        if (j != i) s = s + gj_u100(seed, (u64)i * (u64)n + (u64)j);
-    A[(long long)i * ld + (i - col0)] = (s + gj_u100(seed, (u64)i * (u64)n + (u64)i)) + 1.0f;
+        if (j != i) s = __fadd_rn(s, gj_u100(seed, (u64)i * (u64)n + (u64)j));
+    A[(long long)i * ld + (i - col0)] = __fadd_rn(__fadd_rn(s, gj_u100(seed, (u64)i * (u64)n + (u64)i)), 1.0f);
 }
 
 __global__ void __launch_bounds__(256) generate_batched_kernel(float *__restrict__ A, int n, long long first,
