@@ -1,0 +1,448 @@
+// Panel factorisation, v1: the latency-critical part of the blocked Gauss-Jordan.
+//
+// A 128-wide panel is factored as W-wide sub-panels (W = 16, or 8 for very tall panels):
+//
+//   subpanel_kernel      ONE thread-block cluster (up to 16 CTAs x 512 threads) holds the whole
+//                        n x W sub-panel in REGISTERS and runs its W pivot steps without leaving the
+//                        chip: per step a warp-shuffle arg max, one DSMEM all-to-all of
+//                        (key, candidate row) between the CTAs, one cluster barrier, and the rank-1
+//                        update from registers.  Fuses, per column, the reference's maxPivotKernel +
+//                        finalMaxPivotKernel + pivotElementsKernel + fixRowKernel + fixColumnKernel
+//                        (/root/reference/Matlab/mat_inv_32/mat_inv_32/mat_inv_32.cpp:13-173, launch
+//                        loop :317-362) restricted to the sub-panel columns.
+//   panel_update_kernel  applies the sub-panel's W steps to the other columns of the panel (whole
+//                        GPU): row interchanges, recurrence on the W pivot rows, rank-W update.
+//
+// Row interchanges inside the cluster kernel are IMPLICIT: a row never leaves its registers, each
+// row carries its logical position `lpos` and the swap r <-> p just exchanges two logical positions.
+// Candidates are rows with lpos >= r and ties break on the lowest lpos, so the pivot sequence and
+// every FMA chain are exactly those of the physically swapping algorithm (oracle A.3/A.4).
+//
+// The panel ping-pongs between two buffers per sub-panel (like the reference's two [A|I] buffers,
+// :352-359), so the update kernel never reads a row another CTA has already rewritten.
+#include "common.cuh"
+#include "kernels.h"
+
+#define SP_THREADS 512
+#define SP_MAXCTA 16
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned mapa_shared(const void *p, unsigned cta) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f4(unsigned addr, const float4 &v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+struct __align__(16) SubMail {  // 80 bytes = 5 float4
+    u64 key;
+    u64 pad;
+    float row[16];
+};
+
+struct __align__(16) SubSmem {
+    SubMail mail[2][SP_MAXCTA];  // [step parity][source CTA]  -- written remotely
+    SubMail wcand[SP_THREADS / 32];
+    float u[16];
+    int p;
+    float v;
+    int pad[2];
+    // followed by: float hist[W][R * SP_THREADS]
+};
+
+// ------------------------------------------------------------------------------------------ sub-panel
+template <int W, int R>
+__global__ void __launch_bounds__(SP_THREADS, 1)
+subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict__ out, long long ld_out, int n, int k0,
+                int s0, int sw, float *__restrict__ CmT, long long ldc, int *__restrict__ piv, float *__restrict__ pv,
+                int *__restrict__ info) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SubSmem &s = *reinterpret_cast<SubSmem *>(smem_raw);
+    float *hist = reinterpret_cast<float *>(smem_raw + sizeof(SubSmem));  // [W][R*SP_THREADS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = cluster_ctarank(), nct = cluster_nctarank();
+
+    float x[R][W];
+    int lpos[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+        const int i = (q * (int)nct + (int)rank) * SP_THREADS + tid;
+        lpos[q] = (i < n) ? i : -1;
+        if (i < n) {
+            const float4 *src = reinterpret_cast<const float4 *>(in + (long long)i * ld_in + s0);
+#pragma unroll
+            for (int f = 0; f < W / 4; f++) {
+                const float4 v4 = src[f];
+                x[q][4 * f + 0] = v4.x; x[q][4 * f + 1] = v4.y; x[q][4 * f + 2] = v4.z; x[q][4 * f + 3] = v4.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; j++) x[q][j] = 0.0f;
+        }
+    }
+    // every CTA of the cluster must be resident before anyone writes into its shared memory
+    cluster_arrive();
+    cluster_wait();
+
+#pragma unroll
+    for (int t = 0; t < W; t++) {
+        if (t < sw) {
+            const int r = k0 + s0 + t;
+            // ---- (1) local candidates, warp arg max
+            u64 best = 0;
+            int bq = 0;
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                if (lpos[q] >= r) {
+                    const u64 kk = gj_key(x[q][t], lpos[q], lpos[q] == r);
+                    if (kk > best) { best = kk; bq = q; }
+                }
+            }
+            const u64 wbest = warp_max_u64(best);
+            if (wbest == 0) {
+                if (lane == 0) s.wcand[warp].key = 0;
+            } else if (best == wbest) {  // keys are unique (distinct rows): exactly one lane
+                SubMail &c = s.wcand[warp];
+                c.key = best;
+#pragma unroll
+                for (int q = 0; q < R; q++)
+                    if (q == bq) {
+#pragma unroll
+                        for (int f = 0; f < W / 4; f++)
+                            *reinterpret_cast<float4 *>(&c.row[4 * f]) =
+                                make_float4(x[q][4 * f], x[q][4 * f + 1], x[q][4 * f + 2], x[q][4 * f + 3]);
+                    }
+            }
+            __syncthreads();
+            // ---- (2) warp 0: CTA best, pushed into every CTA's mailbox (DSMEM all-to-all)
+            if (warp == 0) {
+                const u64 k = (lane < SP_THREADS / 32) ? s.wcand[lane].key : 0;
+                const u64 kbest = warp_max_u64(k);
+                const unsigned hit = __ballot_sync(0xffffffffu, k == kbest && lane < SP_THREADS / 32);
+                const int wsrc = __ffs(hit) - 1;
+                const float4 *src = reinterpret_cast<const float4 *>(&s.wcand[wsrc]);
+                const unsigned dst_cta = lane & 15;
+                if (dst_cta < nct) {
+                    const unsigned base = mapa_shared(&s.mail[t & 1][rank], dst_cta);
+                    for (int f = lane >> 4; f < 1 + W / 4; f += 2) st_cluster_f4(base + 16 * f, src[f]);
+                }
+            }
+            cluster_arrive();
+            cluster_wait();
+            // ---- (3) warp 0: cluster best -> pivot row p, value v, normalised pivot row u
+            if (warp == 0) {
+                const u64 k = (lane < (int)nct) ? s.mail[t & 1][lane].key : 0;
+                const u64 kg = warp_max_u64(k);
+                const unsigned hit = __ballot_sync(0xffffffffu, k == kg && lane < (int)nct);
+                const int csrc = __ffs(hit) - 1;
+                const int p = gj_key_row(kg);
+                const float v = gj_key_value(kg);
+                if (lane < W) {
+                    const float rowv = s.mail[t & 1][csrc].row[lane];
+                    s.u[lane] = (lane == t) ? 1.0f / v : rowv / v;
+                }
+                if (lane == 0) {
+                    s.p = p;
+                    s.v = v;
+                    if (rank == 0) {
+                        piv[r] = p;
+                        pv[s0 + t] = v;
+                        if (gj_bad_pivot(v) && *info == 0) *info = r + 1;
+                    }
+                }
+            }
+            __syncthreads();
+            float u[W];
+#pragma unroll
+            for (int f = 0; f < W / 4; f++) {
+                const float4 v4 = *reinterpret_cast<const float4 *>(&s.u[4 * f]);
+                u[4 * f] = v4.x; u[4 * f + 1] = v4.y; u[4 * f + 2] = v4.z; u[4 * f + 3] = v4.w;
+            }
+            const int p = s.p;
+            // ---- (4) implicit swap + rank-1 update from registers; multipliers recorded in smem
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                if (lpos[q] < 0) continue;
+                float c = 0.0f;
+                if (lpos[q] == p) {
+                    lpos[q] = r;
+#pragma unroll
+                    for (int j = 0; j < W; j++) x[q][j] = u[j];
+                } else {
+                    if (lpos[q] == r) lpos[q] = p;
+                    c = x[q][t];
+#pragma unroll
+                    for (int j = 0; j < W; j++)
+                        if (j != t) x[q][j] = gj_elim(x[q][j], c, u[j]);
+                    x[q][t] = fmaf(-c, u[t], 0.0f);
+                }
+                hist[t * (R * SP_THREADS) + q * SP_THREADS + tid] = c;
+            }
+        }
+    }
+
+    // ---- write back at the logical positions
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+        const int i = lpos[q];
+        if (i < 0) continue;
+        float4 *dst = reinterpret_cast<float4 *>(out + (long long)i * ld_out + s0);
+#pragma unroll
+        for (int f = 0; f < W / 4; f++) dst[f] = make_float4(x[q][4 * f], x[q][4 * f + 1], x[q][4 * f + 2], x[q][4 * f + 3]);
+#pragma unroll
+        for (int t = 0; t < W; t++)
+            if (t < sw) CmT[(long long)(s0 + t) * ldc + i] = hist[t * (R * SP_THREADS) + q * SP_THREADS + tid];
+    }
+    // nobody may exit while a peer could still write into its mailbox
+    cluster_arrive();
+    cluster_wait();
+}
+
+// ------------------------------------------------------------------------------------------ update of the rest of the panel
+struct __align__(16) UpdSmem {
+    float old_[32][MATINV_NB];   // original contents of every row touched by the sub-panel's swaps
+    float us[16][MATINV_NB];     // U snapshot of the sub-panel steps
+    float xf[16][MATINV_NB];     // final contents of the sub-panel's pivot rows
+    float cs[16][MATINV_RB];     // multipliers of my 64 rows
+    float cp[16][16];            // multipliers of the pivot rows
+    float pv[16];
+    int pos[32], content[32];
+    int m;
+    int rowmap[MATINV_RB];       // my row -> slot in pos[] or -1
+};
+
+// Net permutation of the sub-panel's sw swaps: pos[idx] = row of slot idx (first sw slots are the
+// pivot rows), content[idx] = slot whose ORIGINAL data ends up in slot idx.  One warp.
+__device__ __forceinline__ void build_subperm(const int *__restrict__ piv, int r0, int sw, int *pos, int *content, int *mout) {
+    const int lane = threadIdx.x & 31;
+    pos[lane] = (lane < sw) ? r0 + lane : -1;
+    content[lane] = lane;
+    __syncwarp();
+    int m = sw;
+    for (int t = 0; t < sw; t++) {
+        const int p = piv[r0 + t];
+        if (p == r0 + t) continue;
+        int b;
+        if (p < r0 + sw) b = p - r0;
+        else {
+            const bool hit = (lane >= sw) && (lane < m) && (pos[lane] == p);
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) b = __ffs(bal) - 1;
+            else {
+                b = m;
+                if (lane == 0) pos[m] = p;
+                m++;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { const int ca = content[t], cb = content[b]; content[t] = cb; content[b] = ca; }
+        __syncwarp();
+    }
+    if (lane == 0) *mout = m;
+}
+
+__global__ void __launch_bounds__(256)
+panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__restrict__ out, long long ld_out, int n,
+                    int k0, int s0, int sw, int wfull, float *__restrict__ CmT, long long ldc,
+                    const int *__restrict__ piv, const float *__restrict__ pvg, PanelState *__restrict__ ps, int kb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UpdSmem &s = *reinterpret_cast<UpdSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = k0 + s0;
+
+    if (blockIdx.x == gridDim.x - 1) {
+        // ===== bookkeeping CTA: whole-panel permutation state + swaps of the earlier multiplier columns
+        int *ppos = reinterpret_cast<int *>(smem_raw);               // [256]
+        int *pcontent = ppos + 2 * MATINV_NB;                         // [256]
+        int *spos = pcontent + 2 * MATINV_NB;                         // [32]
+        int *scontent = spos + 32;                                    // [32]
+        int *sm_m = scontent + 32;                                    // [2]
+        float *oldh = reinterpret_cast<float *>(sm_m + 4);            // [32][s0]
+        for (int i = tid; i < 2 * MATINV_NB; i += 256) {
+            ppos[i] = (s0 == 0) ? k0 + i : ps->pos[i];
+            pcontent[i] = (s0 == 0) ? i : ps->content[i];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int m = (s0 == 0) ? kb : ps->m;
+            for (int t = 0; t < sw; t++) {
+                const int r = r0 + t, p = piv[r];
+                if (p == r) continue;
+                int b = -1;
+                if (p < k0 + kb) b = p - k0;
+                else {
+                    for (int base = kb; base < m; base += 32) {
+                        const int i = base + lane;
+                        const bool hit = (i < m) && (ppos[i] == p);
+                        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                        if (bal) { b = base + (__ffs(bal) - 1); break; }
+                    }
+                    if (b < 0) {
+                        b = m;
+                        if (lane == 0) { ppos[m] = p; pcontent[m] = m; }
+                        m++;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { const int ca = pcontent[s0 + t], cb = pcontent[b]; pcontent[s0 + t] = cb; pcontent[b] = ca; }
+                __syncwarp();
+            }
+            if (lane == 0) ps->m = m;
+        } else if (warp == 1) {
+            build_subperm(piv, r0, sw, spos, scontent, sm_m);
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * MATINV_NB; i += 256) { ps->pos[i] = ppos[i]; ps->content[i] = pcontent[i]; }
+        const int m = sm_m[0];
+        // multipliers recorded by the earlier sub-panels of this panel follow their rows
+        for (int e = tid; e < m * s0; e += 256) {
+            const int idx = e / s0, q = e - idx * s0;
+            oldh[idx * s0 + q] = CmT[(long long)q * ldc + spos[idx]];
+        }
+        __syncthreads();
+        for (int e = tid; e < m * s0; e += 256) {
+            const int idx = e / s0, q = e - idx * s0;
+            const int c = scontent[idx];
+            if (c != idx) CmT[(long long)q * ldc + spos[idx]] = oldh[c * s0 + q];
+        }
+        return;
+    }
+
+    // ===== regular CTA: rows [i0, i0 + 64)
+    const int i0 = blockIdx.x * MATINV_RB;
+    if (warp == 0) build_subperm(piv, r0, sw, s.pos, s.content, &s.m);
+    for (int e = tid; e < 16 * MATINV_RB; e += 256) {
+        const int t = e / MATINV_RB, ii = e - t * MATINV_RB;
+        s.cs[t][ii] = (t < sw && i0 + ii < n) ? CmT[(long long)(s0 + t) * ldc + i0 + ii] : 0.0f;
+    }
+    {
+        const int t = tid >> 4, t2 = tid & 15;
+        s.cp[t][t2] = (t < sw && t2 < sw) ? CmT[(long long)(s0 + t) * ldc + r0 + t2] : 0.0f;
+        if (tid < 16) s.pv[tid] = (tid < sw) ? pvg[s0 + tid] : 1.0f;
+        if (tid < MATINV_RB) s.rowmap[tid] = -1;
+    }
+    __syncthreads();
+    const int m = s.m;
+    if (tid < m) {
+        const int ii = s.pos[tid] - i0;
+        if (ii >= 0 && ii < MATINV_RB) s.rowmap[ii] = tid;
+    }
+    for (int e = tid; e < m * 32; e += 256) {
+        const int idx = e >> 5, f = e & 31;
+        *reinterpret_cast<float4 *>(&s.old_[idx][4 * f]) =
+            *reinterpret_cast<const float4 *>(in + (long long)s.pos[idx] * ld_in + 4 * f);
+    }
+    __syncthreads();
+    // recurrence on the sw pivot rows, one thread per panel column
+    if (tid < MATINV_NB) {
+        float xx[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) xx[t] = (t < sw) ? s.old_[s.content[t]][tid] : 0.0f;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            if (t < sw) {
+                const float u = xx[t] / s.pv[t];
+                s.us[t][tid] = u;
+                xx[t] = u;
+#pragma unroll
+                for (int t2 = 0; t2 < 16; t2++)
+                    if (t2 != t && t2 < sw) xx[t2] = gj_elim(xx[t2], s.cp[t][t2], u);
+            } else {
+                s.us[t][tid] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 16; t++) s.xf[t][tid] = xx[t];
+    }
+    __syncthreads();
+
+    const bool own_cols = (lane >= (s0 >> 2)) && (lane < ((s0 + wfull) >> 2));  // the sub-panel's own columns
+    float4 us[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) us[t] = *reinterpret_cast<const float4 *>(&s.us[t][4 * lane]);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int ii = warp * 8 + q, i = i0 + ii;
+        if (i >= n) continue;  // warp-uniform
+        float4 acc;
+        if (i >= r0 && i < r0 + sw) {
+            acc = *reinterpret_cast<const float4 *>(&s.xf[i - r0][4 * lane]);
+        } else {
+            const int slot = s.rowmap[ii];
+            if (slot >= 0) acc = *reinterpret_cast<const float4 *>(&s.old_[s.content[slot]][4 * lane]);
+            else acc = *reinterpret_cast<const float4 *>(in + (long long)i * ld_in + 4 * lane);
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                const float c = s.cs[t][ii];  // zero beyond sw: fma(-0, 0, a) == a
+                acc.x = gj_elim(acc.x, c, us[t].x);
+                acc.y = gj_elim(acc.y, c, us[t].y);
+                acc.z = gj_elim(acc.z, c, us[t].z);
+                acc.w = gj_elim(acc.w, c, us[t].w);
+            }
+        }
+        if (!own_cols) *reinterpret_cast<float4 *>(out + (long long)i * ld_out + 4 * lane) = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+template <int W, int R>
+static cudaError_t launch_subpanel_t(int ncta, const float *in, long long ld_in, float *out, long long ld_out, int n,
+                                     int k0, int s0, int sw, float *CmT, long long ldc, int *piv, float *pv, int *info,
+                                     cudaStream_t st) {
+    const size_t smem = sizeof(SubSmem) + (size_t)W * R * SP_THREADS * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(subpanel_kernel<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(subpanel_kernel<W, R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncta);
+    cfg.blockDim = dim3(SP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, subpanel_kernel<W, R>, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info);
+}
+
+int subpanel_width(int n) { return (n > 32768) ? 8 : 16; }
+bool subpanel_supported(int n) { return n <= 65536; }
+
+cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0,
+                            int sw, float *CmT, long long ldc, int *piv, float *pv, int *info, cudaStream_t st) {
+    if (n <= 8192) {
+        int ncta = 1;
+        while (ncta * SP_THREADS < n) ncta *= 2;
+        return launch_subpanel_t<16, 1>(ncta, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
+    }
+    if (n <= 16384) return launch_subpanel_t<16, 2>(16, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
+    if (n <= 32768) return launch_subpanel_t<16, 4>(16, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
+    return launch_subpanel_t<8, 8>(16, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
+}
+
+void launch_panel_update(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0, int sw,
+                         int wfull, float *CmT, long long ldc, const int *piv, const float *pv, PanelState *ps, int kb,
+                         cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem));
+        configured = true;
+    }
+    const int nblk = (n + MATINV_RB - 1) / MATINV_RB + 1;
+    panel_update_kernel<<<nblk, 256, sizeof(UpdSmem), st>>>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv,
+                                                            pv, ps, kb);
+}

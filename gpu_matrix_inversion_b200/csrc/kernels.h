@@ -25,6 +25,15 @@ void launch_panel_step(const float *in, long long ld_in, float *out, long long l
                        const u64 *part_in, int nparts, u64 *part_out, float *CmT, long long ldc, int *piv, float *pv,
                        int *info, PanelState *ps, cudaStream_t st);
 
+// ---- gj_subpanel.cu : panel factorisation v1 (cluster/DSMEM sub-panel kernel + in-panel update)
+int subpanel_width(int n);
+bool subpanel_supported(int n);
+cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0,
+                            int sw, float *CmT, long long ldc, int *piv, float *pv, int *info, cudaStream_t st);
+void launch_panel_update(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0, int sw,
+                         int wfull, float *CmT, long long ldc, const int *piv, const float *pv, PanelState *ps, int kb,
+                         cudaStream_t st);
+
 // ---- gj_rowblock.cu : row interchanges + row-block recurrence on all non-panel columns
 void launch_rowblock(float *W, long long ld, int ncols_pad, int k0, int kb, const float *CmT, long long ldc,
                      const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st);

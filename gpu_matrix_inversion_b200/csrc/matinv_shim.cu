@@ -156,26 +156,65 @@ void schedule_unblocked(Workspace &w, int n, cudaStream_t st) {
     }
 }
 
+// Panel factorisation v0: one fused launch per column (gj_panel.cu).
+void panel_v0(Workspace &w, int n, int k0, int kb, cudaStream_t st) {
+    const long long ld = w.npad;
+    const int nparts = (n + MATINV_RB - 1) / MATINV_RB;
+    launch_argmax_col(w.W, ld, n, k0, k0, w.part[0], nparts, st);
+    COUNT_LAUNCH(1 + kb);
+    for (int t = 0; t < kb; t++) {
+        const float *in = (t == 0) ? w.W + k0 : w.P[(t - 1) & 1];
+        const long long ld_in = (t == 0) ? ld : MATINV_NB;
+        const bool last = (t == kb - 1) && kb > 1;
+        float *out = last ? w.W + k0 : w.P[t & 1];
+        const long long ld_out = last ? ld : MATINV_NB;
+        launch_panel_step(in, ld_in, out, ld_out, n, kb, t, k0, w.part[t & 1], nparts, w.part[(t + 1) & 1], w.CmT, ld,
+                          w.piv, w.pv, w.info, w.ps, st);
+    }
+    if (kb == 1)  // single-column panel: in == out would alias, so it went through P[0]
+        cudaMemcpy2DAsync(w.W + k0, ld * sizeof(float), w.P[0], MATINV_NB * sizeof(float), MATINV_NB * sizeof(float), n,
+                          cudaMemcpyDeviceToDevice, st);
+}
+
+// Panel factorisation v1: cluster sub-panel kernel + in-panel update (gj_subpanel.cu).
+void panel_v1(Workspace &w, int n, int k0, int kb, cudaStream_t st) {
+    const long long ld = w.npad;
+    const int sub = subpanel_width(n);
+    const int ns = (kb + sub - 1) / sub;
+    for (int s = 0; s < ns; s++) {
+        const int s0 = s * sub;
+        const int sw = (kb - s0 < sub) ? kb - s0 : sub;
+        const float *in = (s == 0) ? w.W + k0 : w.P[(s - 1) & 1];
+        const long long ld_in = (s == 0) ? ld : MATINV_NB;
+        const bool to_w = (s == ns - 1) && ns > 1;
+        float *out = to_w ? w.W + k0 : w.P[s & 1];
+        const long long ld_out = to_w ? ld : MATINV_NB;
+        launch_subpanel(in, ld_in, out, ld_out, n, k0, s0, sw, w.CmT, ld, w.piv, w.pv, w.info, st);
+        launch_panel_update(in, ld_in, out, ld_out, n, k0, s0, sw, sub, w.CmT, ld, w.piv, w.pv, w.ps, kb, st);
+        COUNT_LAUNCH(2);
+    }
+    if (ns == 1)
+        cudaMemcpy2DAsync(w.W + k0, ld * sizeof(float), w.P[0], MATINV_NB * sizeof(float), MATINV_NB * sizeof(float), n,
+                          cudaMemcpyDeviceToDevice, st);
+}
+
+bool use_panel_v1(int n) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("MATINV_PANEL");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode == 1 && subpanel_supported(n);
+}
+
 // Blocked right-looking: per 128-wide panel  factor -> (swaps + recurrence) -> trailing GEMM.
 void schedule_blocked(Workspace &w, int n, cudaStream_t st) {
     const long long ld = w.npad;
-    const int nparts = (n + MATINV_RB - 1) / MATINV_RB;
+    const bool v1 = use_panel_v1(n);
     for (int k0 = 0; k0 < n; k0 += MATINV_NB) {
         const int kb = (n - k0 < MATINV_NB) ? n - k0 : MATINV_NB;
-        launch_argmax_col(w.W, ld, n, k0, k0, w.part[0], nparts, st);
-        COUNT_LAUNCH(1 + kb);
-        for (int t = 0; t < kb; t++) {
-            const float *in = (t == 0) ? w.W + k0 : w.P[(t - 1) & 1];
-            const long long ld_in = (t == 0) ? ld : MATINV_NB;
-            const bool last = (t == kb - 1) && kb > 1;
-            float *out = last ? w.W + k0 : w.P[t & 1];
-            const long long ld_out = last ? ld : MATINV_NB;
-            launch_panel_step(in, ld_in, out, ld_out, n, kb, t, k0, w.part[t & 1], nparts, w.part[(t + 1) & 1], w.CmT,
-                              ld, w.piv, w.pv, w.info, w.ps, st);
-        }
-        if (kb == 1)  // single-column panel: in == out would alias, so it went through P[0]
-            cudaMemcpy2DAsync(w.W + k0, ld * sizeof(float), w.P[0], MATINV_NB * sizeof(float),
-                              MATINV_NB * sizeof(float), n, cudaMemcpyDeviceToDevice, st);
+        if (v1) panel_v1(w, n, k0, kb, st);
+        else panel_v0(w, n, k0, kb, st);
         if (w.npad > MATINV_NB) {
             launch_rowblock(w.W, ld, w.npad, k0, kb, w.CmT, ld, w.pv, w.ps, w.U, ld, st);
             if (g_prof.on) cudaEventRecord(prof_event(), st);
