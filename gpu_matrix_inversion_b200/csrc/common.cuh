@@ -22,6 +22,15 @@ __device__ __forceinline__ u64 gj_key(float x, int row, bool incumbent) {
     const unsigned int lo = ((0x7FFFFFFFu - (unsigned int)row) << 1) | (__float_as_uint(x) >> 31);
     return ((u64)b << 32) | (u64)lo;
 }
+// The same key built from its parts (magnitude bits with the NaN rules, row, value for the sign).
+__device__ __forceinline__ unsigned gj_mag(float x, bool incumbent) {
+    const float a = fabsf(x);
+    return (a == a) ? __float_as_uint(a) : (incumbent ? 0xFFFFFFFFu : 0u);
+}
+__device__ __forceinline__ u64 gj_key_from(unsigned mag, int row, float x) {
+    const unsigned int lo = ((0x7FFFFFFFu - (unsigned int)row) << 1) | (__float_as_uint(x) >> 31);
+    return ((u64)mag << 32) | (u64)lo;
+}
 __device__ __forceinline__ int gj_key_row(u64 k) { return (int)(0x7FFFFFFFu - ((unsigned int)(k & 0xFFFFFFFFull) >> 1)); }
 __device__ __forceinline__ float gj_key_value(u64 k) {
     const unsigned int b = (unsigned int)(k >> 32);

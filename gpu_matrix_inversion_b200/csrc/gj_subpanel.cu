@@ -92,29 +92,34 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
     cluster_arrive();
     cluster_wait();
 
-#pragma unroll
+    // The step loop is ROLLED (one copy of the body stays in the instruction cache): after every step
+    // the register window rotates left by one column, so the current column is always x[.][0] and the
+    // freshly produced inverse column enters at x[.][W-1]; after W steps the window is back in place.
+#pragma unroll 1
     for (int t = 0; t < W; t++) {
         if (t < sw) {
             const int r = k0 + s0 + t;
-            // ---- (1) local candidates, warp arg max
-            u64 best = 0;
-            int bq = 0;
+            // ---- (1) local candidates, warp arg max (two redux.sync: magnitude, then lowest position)
+            unsigned mag = 0;
+            int cand = 0x7FFFFFFF, bq = -1;
 #pragma unroll
             for (int q = 0; q < R; q++) {
                 if (lpos[q] >= r) {
-                    const u64 kk = gj_key(x[q][t], lpos[q], lpos[q] == r);
-                    if (kk > best) { best = kk; bq = q; }
+                    const unsigned mq = gj_mag(x[q][0], lpos[q] == r);
+                    if (bq < 0 || mq > mag || (mq == mag && lpos[q] < cand)) { mag = mq; cand = lpos[q]; bq = q; }
                 }
             }
-            const u64 wbest = warp_max_u64(best);
-            if (wbest == 0) {
+            const bool has = bq >= 0;
+            const unsigned gm = __reduce_max_sync(0xffffffffu, has ? mag : 0u);
+            const unsigned pw = __reduce_min_sync(0xffffffffu, (has && mag == gm) ? (unsigned)cand : 0x7FFFFFFFu);
+            if (pw == 0x7FFFFFFFu) {
                 if (lane == 0) s.wcand[warp].key = 0;
-            } else if (best == wbest) {  // keys are unique (distinct rows): exactly one lane
+            } else if (has && mag == gm && (unsigned)cand == pw) {  // exactly one lane: positions are distinct
                 SubMail &c = s.wcand[warp];
-                c.key = best;
 #pragma unroll
                 for (int q = 0; q < R; q++)
                     if (q == bq) {
+                        c.key = gj_key_from(mag, cand, x[q][0]);
 #pragma unroll
                         for (int f = 0; f < W / 4; f++)
                             *reinterpret_cast<float4 *>(&c.row[4 * f]) =
@@ -124,9 +129,12 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
             __syncthreads();
             // ---- (2) warp 0: CTA best, pushed into every CTA's mailbox (DSMEM all-to-all)
             if (warp == 0) {
-                const u64 k = (lane < SP_THREADS / 32) ? s.wcand[lane].key : 0;
-                const u64 kbest = warp_max_u64(k);
-                const unsigned hit = __ballot_sync(0xffffffffu, k == kbest && lane < SP_THREADS / 32);
+                const bool inr = lane < SP_THREADS / 32;
+                const u64 k = inr ? s.wcand[lane].key : 0;
+                const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+                const unsigned ghi = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned glo = __reduce_max_sync(0xffffffffu, (inr && hi == ghi) ? lo : 0u);
+                const unsigned hit = __ballot_sync(0xffffffffu, inr && hi == ghi && lo == glo);
                 const int wsrc = __ffs(hit) - 1;
                 const float4 *src = reinterpret_cast<const float4 *>(&s.wcand[wsrc]);
                 const unsigned dst_cta = lane & 15;
@@ -137,21 +145,24 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
             }
             cluster_arrive();
             cluster_wait();
-            // ---- (3) warp 0: cluster best -> pivot row p, value v, normalised pivot row u
+            // ---- (3) warp 0: cluster best -> pivot row p, value v, normalised pivot row u (rotated)
             if (warp == 0) {
-                const u64 k = (lane < (int)nct) ? s.mail[t & 1][lane].key : 0;
-                const u64 kg = warp_max_u64(k);
-                const unsigned hit = __ballot_sync(0xffffffffu, k == kg && lane < (int)nct);
+                const bool inr = lane < (int)nct;
+                const u64 k = inr ? s.mail[t & 1][lane].key : 0;
+                const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+                const unsigned ghi = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned glo = __reduce_max_sync(0xffffffffu, (inr && hi == ghi) ? lo : 0u);
+                const unsigned hit = __ballot_sync(0xffffffffu, inr && hi == ghi && lo == glo);
                 const int csrc = __ffs(hit) - 1;
+                const u64 kg = ((u64)ghi << 32) | glo;
                 const int p = gj_key_row(kg);
                 const float v = gj_key_value(kg);
                 if (lane < W) {
                     const float rowv = s.mail[t & 1][csrc].row[lane];
-                    s.u[lane] = (lane == t) ? 1.0f / v : rowv / v;
+                    s.u[(lane + W - 1) % W] = (lane == 0) ? 1.0f / v : rowv / v;
                 }
                 if (lane == 0) {
                     s.p = p;
-                    s.v = v;
                     if (rank == 0) {
                         piv[r] = p;
                         pv[s0 + t] = v;
@@ -178,13 +189,21 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
                     for (int j = 0; j < W; j++) x[q][j] = u[j];
                 } else {
                     if (lpos[q] == r) lpos[q] = p;
-                    c = x[q][t];
+                    c = x[q][0];
 #pragma unroll
-                    for (int j = 0; j < W; j++)
-                        if (j != t) x[q][j] = gj_elim(x[q][j], c, u[j]);
-                    x[q][t] = fmaf(-c, u[t], 0.0f);
+                    for (int j = 0; j < W - 1; j++) x[q][j] = gj_elim(x[q][j + 1], c, u[j]);
+                    x[q][W - 1] = fmaf(-c, u[W - 1], 0.0f);
                 }
                 hist[t * (R * SP_THREADS) + q * SP_THREADS + tid] = c;
+            }
+        } else {
+            // partial sub-panel (last panel only): pure rotation keeps the window aligned
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                const float x0 = x[q][0];
+#pragma unroll
+                for (int j = 0; j < W - 1; j++) x[q][j] = x[q][j + 1];
+                x[q][W - 1] = x0;
             }
         }
     }
@@ -227,8 +246,9 @@ __device__ __forceinline__ void build_subperm(const int *__restrict__ piv, int r
     content[lane] = lane;
     __syncwarp();
     int m = sw;
+    const int pl = (lane < sw) ? piv[r0 + lane] : 0;  // one coalesced read instead of sw dependent ones
     for (int t = 0; t < sw; t++) {
-        const int p = piv[r0 + t];
+        const int p = __shfl_sync(0xffffffffu, pl, t);
         if (p == r0 + t) continue;
         int b;
         if (p < r0 + sw) b = p - r0;
@@ -273,8 +293,9 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
         __syncthreads();
         if (warp == 0) {
             int m = (s0 == 0) ? kb : ps->m;
+            const int pl = (lane < sw) ? piv[r0 + lane] : 0;
             for (int t = 0; t < sw; t++) {
-                const int r = r0 + t, p = piv[r];
+                const int r = r0 + t, p = __shfl_sync(0xffffffffu, pl, t);
                 if (p == r) continue;
                 int b = -1;
                 if (p < k0 + kb) b = p - k0;
@@ -341,22 +362,26 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
             *reinterpret_cast<const float4 *>(in + (long long)s.pos[idx] * ld_in + 4 * f);
     }
     __syncthreads();
-    // recurrence on the sw pivot rows, one thread per panel column
+    // recurrence on the sw pivot rows, one thread per panel column.  Rolled loop + rotating register
+    // window (the current pivot row is always xx[0]), see subpanel_kernel.
     if (tid < MATINV_NB) {
         float xx[16];
 #pragma unroll
         for (int t = 0; t < 16; t++) xx[t] = (t < sw) ? s.old_[s.content[t]][tid] : 0.0f;
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < 16; t++) {
             if (t < sw) {
-                const float u = xx[t] / s.pv[t];
+                const float u = xx[0] / s.pv[t];
                 s.us[t][tid] = u;
-                xx[t] = u;
 #pragma unroll
-                for (int t2 = 0; t2 < 16; t2++)
-                    if (t2 != t && t2 < sw) xx[t2] = gj_elim(xx[t2], s.cp[t][t2], u);
+                for (int j = 0; j < 15; j++) xx[j] = gj_elim(xx[j + 1], s.cp[t][(t + 1 + j) & 15], u);
+                xx[15] = u;
             } else {
                 s.us[t][tid] = 0.0f;
+                const float x0 = xx[0];
+#pragma unroll
+                for (int j = 0; j < 15; j++) xx[j] = xx[j + 1];
+                xx[15] = x0;
             }
         }
 #pragma unroll
@@ -368,7 +393,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
     float4 us[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) us[t] = *reinterpret_cast<const float4 *>(&s.us[t][4 * lane]);
-#pragma unroll
+#pragma unroll 2
     for (int q = 0; q < 8; q++) {
         const int ii = warp * 8 + q, i = i0 + ii;
         if (i >= n) continue;  // warp-uniform
