@@ -36,7 +36,7 @@ EXPORTS = [
     "matinv_shard_destroy", "matinv_shard_local", "matinv_shard_generate", "matinv_shard_factor",
     "matinv_shard_apply", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
-    "matinv_profile_read",
+    "matinv_profile_read", "matinv_debug_trace",
 ]
 
 
@@ -70,6 +70,8 @@ def _load() -> ctypes.CDLL:
     L.matinv_profile_enable.restype = None
     L.matinv_profile_read.argtypes = [dp, ctypes.POINTER(ll), dp, ctypes.POINTER(ll)]
     L.matinv_profile_read.restype = i
+    L.matinv_debug_trace.argtypes = [i, ctypes.c_void_p]
+    L.matinv_debug_trace.restype = i
     L.matinv_shard_panel_bytes.argtypes = [i]
     L.matinv_shard_panel_bytes.restype = ll
     L.matinv_shard_create.argtypes = [i, i, i, ctypes.POINTER(vp)]

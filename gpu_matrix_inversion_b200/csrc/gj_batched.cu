@@ -7,6 +7,7 @@
 // v0 layout: a[n][n+1] floats in shared memory, 256 threads, three barriers per column.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 __global__ void __launch_bounds__(256)
 batched_smem_kernel(const float *__restrict__ A, int n, long long batch, float *__restrict__ X,
@@ -100,7 +101,185 @@ batched_smem_kernel(const float *__restrict__ A, int n, long long batch, float *
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v1: ONE WARP PER MATRIX, matrix resident in REGISTERS (n = 64: lane l owns physical rows l and
+// l+32, 128 registers; n = 32: one row per lane).
+//   * row interchanges are implicit (each row carries its logical position, see gj_subpanel.cu)
+//   * the column window rotates left by one per step, so the step loop is rolled and every register
+//     index is static: the current column is always a[.][0], the new inverse column enters at N-1
+//   * pivot search: two redux.sync; pivot row broadcast and the distributed true division go through
+//     2 x N floats of shared memory; the rank-1 update is N FFMA per owned row
+//   * the deferred column permutation is kept incrementally (qinv) and applied when the result is
+//     staged through shared memory for coalesced stores
+template <int N>
+__global__ void __launch_bounds__(128, 2)
+batched_reg_kernel(const float *__restrict__ A, long long batch, float *__restrict__ X, int *__restrict__ info) {
+    constexpr int RS = N / 32;
+    constexpr int LD = N + 1;
+    constexpr int PER_WARP = ((N * LD + N + 3) / 4) * 4;  // floats; keeps every warp's base 16-byte aligned
+    extern __shared__ __align__(16) float smem_f[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *stage = smem_f + warp * PER_WARP;
+    float *raw = stage, *urot = stage + N;
+    int *qinv = reinterpret_cast<int *>(stage + N * LD);
+    const unsigned urot_s = (unsigned)__cvta_generic_to_shared(urot);
+
+    for (long long b = (long long)blockIdx.x * 4 + warp; b < batch; b += (long long)gridDim.x * 4) {
+        const float *Ab = A + b * (long long)(N * N);
+        float a[RS][N];
+        int lpos[RS];
+        bool used[RS];
+#pragma unroll
+        for (int s = 0; s < RS; s++) {
+            const float4 *src = reinterpret_cast<const float4 *>(Ab + (s * 32 + lane) * N);
+#pragma unroll
+            for (int f = 0; f < N / 4; f++) {
+                const float4 v4 = src[f];
+                a[s][4 * f] = v4.x; a[s][4 * f + 1] = v4.y; a[s][4 * f + 2] = v4.z; a[s][4 * f + 3] = v4.w;
+            }
+            lpos[s] = s * 32 + lane;
+            used[s] = false;
+            qinv[s * 32 + lane] = s * 32 + lane;
+        }
+        int sinfo = 0;
+        __syncwarp();
+
+#pragma unroll 1
+        for (int r = 0; r < N; r++) {
+            // ---- (1) pivot search over the not-yet-used rows (== logical positions >= r)
+            unsigned mag = 0;
+            int cand = 0x7FFFFFFF;
+            bool has = false;
+#pragma unroll
+            for (int s = 0; s < RS; s++) {
+                if (!used[s]) {
+                    const unsigned mq = gj_mag(a[s][0], lpos[s] == r);
+                    if (!has || mq > mag || (mq == mag && lpos[s] < cand)) { mag = mq; cand = lpos[s]; has = true; }
+                }
+            }
+            const unsigned gm = __reduce_max_sync(0xffffffffu, has ? mag : 0u);
+            const int p = (int)__reduce_min_sync(0xffffffffu, (has && mag == gm) ? (unsigned)cand : 0x7FFFFFFFu);
+            bool own[RS];
+#pragma unroll
+            for (int s = 0; s < RS; s++) own[s] = !used[s] && lpos[s] == p;
+            const unsigned b0 = __ballot_sync(0xffffffffu, own[0]);
+            unsigned b1 = 0;
+            if (RS > 1) b1 = __ballot_sync(0xffffffffu, own[RS - 1]);
+            const int Sp = b0 ? 0 : 1;                       // warp-uniform slot of the pivot row
+            const int Lp = __ffs(b0 ? b0 : b1) - 1;          // its lane
+            const float v = __shfl_sync(0xffffffffu, (Sp == 0) ? a[0][0] : a[RS - 1][0], Lp);
+            if (gj_bad_pivot(v) && sinfo == 0) sinfo = r + 1;
+            // ---- (2) publish the raw pivot row
+            if (lane == Lp) {
+                if (Sp == 0) {
+#pragma unroll
+                    for (int f = 0; f < N / 4; f++)
+                        reinterpret_cast<float4 *>(raw)[f] = make_float4(a[0][4 * f], a[0][4 * f + 1], a[0][4 * f + 2], a[0][4 * f + 3]);
+                } else {
+#pragma unroll
+                    for (int f = 0; f < N / 4; f++)
+                        reinterpret_cast<float4 *>(raw)[f] =
+                            make_float4(a[RS - 1][4 * f], a[RS - 1][4 * f + 1], a[RS - 1][4 * f + 2], a[RS - 1][4 * f + 3]);
+                }
+            }
+            __syncwarp();
+            // ---- (3) true division, RS elements per lane, stored rotated (position j -> j-1, inverse -> N-1)
+#pragma unroll
+            for (int k = 0; k < RS; k++) {
+                const int pos = lane * RS + k;
+                const float val = raw[pos];
+                urot[(pos + N - 1) % N] = (pos == 0) ? 1.0f / v : val / v;
+            }
+            __syncwarp();
+            // ---- (4) rank-1 update with rotation
+            float u[N];
+#pragma unroll
+            for (int f = 0; f < N / 4; f++) {
+                const float4 v4 = reinterpret_cast<const float4 *>(urot)[f];
+                u[4 * f] = v4.x; u[4 * f + 1] = v4.y; u[4 * f + 2] = v4.z; u[4 * f + 3] = v4.w;
+            }
+#pragma unroll
+            for (int s = 0; s < RS; s++) {
+                if (s == Sp && lane == Lp) {
+                    // the pivot row becomes u: reloaded with LDS.128 (cheaper than N predicated moves)
+#pragma unroll
+                    for (int f = 0; f < N / 4; f++)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(a[s][4 * f]), "=f"(a[s][4 * f + 1]), "=f"(a[s][4 * f + 2]), "=f"(a[s][4 * f + 3])
+                                     : "r"(urot_s + 16 * f));
+                } else {
+                    const float c = a[s][0];
+#pragma unroll
+                    for (int j = 0; j < N - 1; j++) a[s][j] = gj_elim(a[s][j + 1], c, u[j]);
+                    a[s][N - 1] = fmaf(-c, u[N - 1], 0.0f);
+                }
+            }
+            // ---- (5) bookkeeping: logical positions, column permutation
+#pragma unroll
+            for (int s = 0; s < RS; s++) {
+                if (own[s]) { used[s] = true; lpos[s] = r; }
+                else if (!used[s] && lpos[s] == r) lpos[s] = p;
+            }
+            if (lane == 0) { const int q1 = qinv[r], q2 = qinv[p]; qinv[r] = q2; qinv[p] = q1; }
+            __syncwarp();
+        }
+
+        // ---- result: X[lpos][qinv[c]] = a[.][c], staged through shared memory for coalesced stores
+#pragma unroll
+        for (int s = 0; s < RS; s++) {
+            float *row = stage + lpos[s] * LD;
+#pragma unroll
+            for (int c = 0; c < N; c++) row[qinv[c]] = a[s][c];
+        }
+        __syncwarp();
+        float *Xb = X + b * (long long)(N * N);
+        bool bad = false;
+#pragma unroll 4
+        for (int i = 0; i < N; i++) {
+#pragma unroll
+            for (int k = 0; k < RS; k++) {
+                const float xv = stage[i * LD + lane + 32 * k];
+                bad |= !isfinite(xv);
+                Xb[i * N + lane + 32 * k] = xv;
+            }
+        }
+        const int anybad = __any_sync(0xffffffffu, bad);
+        if (lane == 0 && info) info[b] = sinfo ? sinfo : (anybad ? -1 : 0);
+        __syncwarp();
+    }
+}
+
+template <int N>
+static cudaError_t launch_batched_reg(const float *A, long long batch, float *X, int *info, cudaStream_t st) {
+    constexpr int PER_WARP = ((N * (N + 1) + N + 3) / 4) * 4;
+    const size_t smem = 4 * PER_WARP * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(batched_reg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    long long grid = (batch + 3) / 4;
+    const long long cap = 148ll * 2 * 16;
+    if (grid > cap) grid = cap;
+    batched_reg_kernel<N><<<(unsigned)grid, 128, smem, st>>>(A, batch, X, info);
+    return cudaGetLastError();
+}
+
+static bool batched_use_reg() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("MATINV_BATCHED");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode == 1;
+}
+
 cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st) {
+    if (batched_use_reg()) {
+        if (n == 64) return launch_batched_reg<64>(A, batch, X, info, st);
+        if (n == 32) return launch_batched_reg<32>(A, batch, X, info, st);
+    }
     const size_t smem = ((size_t)n * (n + 1) + 3 * (size_t)n) * sizeof(float);
     static bool configured = false;
     if (!configured) {

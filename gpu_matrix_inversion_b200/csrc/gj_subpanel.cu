@@ -26,6 +26,11 @@
 #define SP_THREADS 512
 #define SP_MAXCTA 16
 
+// Optional in-kernel timeline (SM clock) of the LAST launch, for tuning: matinv_debug_trace().
+__device__ int g_trace_on = 0;
+__device__ long long g_trace[128];
+#define TRACE(cond, slot) do { if (trace_on && (cond) && threadIdx.x == 0) g_trace[slot] = clock64(); } while (0)
+
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -69,6 +74,8 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
     float *hist = reinterpret_cast<float *>(smem_raw + sizeof(SubSmem));  // [W][R*SP_THREADS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rank = cluster_ctarank(), nct = cluster_nctarank();
+    const int trace_on = g_trace_on;
+    TRACE(rank == 0, 0);
 
     float x[R][W];
     int lpos[R];
@@ -88,9 +95,11 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
             for (int j = 0; j < W; j++) x[q][j] = 0.0f;
         }
     }
+    TRACE(rank == 0, 1);
     // every CTA of the cluster must be resident before anyone writes into its shared memory
     cluster_arrive();
     cluster_wait();
+    TRACE(rank == 0, 2);
 
     // The step loop is ROLLED (one copy of the body stays in the instruction cache): after every step
     // the register window rotates left by one column, so the current column is always x[.][0] and the
@@ -196,6 +205,7 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
                 }
                 hist[t * (R * SP_THREADS) + q * SP_THREADS + tid] = c;
             }
+            TRACE(rank == 0, 3 + t);
         } else {
             // partial sub-panel (last panel only): pure rotation keeps the window aligned
 #pragma unroll
@@ -220,9 +230,11 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
         for (int t = 0; t < W; t++)
             if (t < sw) CmT[(long long)(s0 + t) * ldc + i] = hist[t * (R * SP_THREADS) + q * SP_THREADS + tid];
     }
+    TRACE(rank == 0, 20);
     // nobody may exit while a peer could still write into its mailbox
     cluster_arrive();
     cluster_wait();
+    TRACE(rank == 0, 21);
 }
 
 // ------------------------------------------------------------------------------------------ update of the rest of the panel
@@ -277,6 +289,9 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
     UpdSmem &s = *reinterpret_cast<UpdSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = k0 + s0;
+    const int trace_on = g_trace_on;
+    TRACE(blockIdx.x == 3, 32);
+    TRACE(blockIdx.x == gridDim.x - 1, 48);
 
     if (blockIdx.x == gridDim.x - 1) {
         // ===== bookkeeping CTA: whole-panel permutation state + swaps of the earlier multiplier columns
@@ -323,6 +338,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
         __syncthreads();
         for (int i = tid; i < 2 * MATINV_NB; i += 256) { ps->pos[i] = ppos[i]; ps->content[i] = pcontent[i]; }
         const int m = sm_m[0];
+        TRACE(true, 49);
         // multipliers recorded by the earlier sub-panels of this panel follow their rows
         for (int e = tid; e < m * s0; e += 256) {
             const int idx = e / s0, q = e - idx * s0;
@@ -334,6 +350,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
             const int c = scontent[idx];
             if (c != idx) CmT[(long long)q * ldc + spos[idx]] = oldh[c * s0 + q];
         }
+        TRACE(true, 50);
         return;
     }
 
@@ -351,6 +368,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
         if (tid < MATINV_RB) s.rowmap[tid] = -1;
     }
     __syncthreads();
+    TRACE(blockIdx.x == 3, 33);
     const int m = s.m;
     if (tid < m) {
         const int ii = s.pos[tid] - i0;
@@ -362,6 +380,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
             *reinterpret_cast<const float4 *>(in + (long long)s.pos[idx] * ld_in + 4 * f);
     }
     __syncthreads();
+    TRACE(blockIdx.x == 3, 34);
     // recurrence on the sw pivot rows, one thread per panel column.  Rolled loop + rotating register
     // window (the current pivot row is always xx[0]), see subpanel_kernel.
     if (tid < MATINV_NB) {
@@ -389,6 +408,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
     }
     __syncthreads();
 
+    TRACE(blockIdx.x == 3, 35);
     const bool own_cols = (lane >= (s0 >> 2)) && (lane < ((s0 + wfull) >> 2));  // the sub-panel's own columns
     float4 us[16];
 #pragma unroll
@@ -415,6 +435,13 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
         }
         if (!own_cols) *reinterpret_cast<float4 *>(out + (long long)i * ld_out + 4 * lane) = acc;
     }
+    TRACE(blockIdx.x == 3, 36);
+}
+
+cudaError_t debug_trace(int on, long long *out128) {
+    cudaError_t e = cudaMemcpyToSymbol(g_trace_on, &on, sizeof(int));
+    if (e == cudaSuccess && out128) e = cudaMemcpyFromSymbol(out128, g_trace, sizeof(long long) * 128);
+    return e;
 }
 
 // ------------------------------------------------------------------------------------------ launchers

@@ -34,6 +34,8 @@ void launch_panel_update(const float *in, long long ld_in, float *out, long long
                          int wfull, float *CmT, long long ldc, const int *piv, const float *pv, PanelState *ps, int kb,
                          cudaStream_t st);
 
+cudaError_t debug_trace(int on, long long *out128);
+
 // ---- gj_rowblock.cu : row interchanges + row-block recurrence on all non-panel columns
 void launch_rowblock(float *W, long long ld, int ncols_pad, int k0, int kb, const float *CmT, long long ldc,
                      const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st);

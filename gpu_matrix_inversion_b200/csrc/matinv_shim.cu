@@ -440,6 +440,15 @@ int matinv_profile_read(double *gemm_ms, long long *gemm_launches, double *gemm_
     return MATINV_OK;
 }
 
+int matinv_debug_trace(int on, long long *out128) {
+    g_err[0] = 0;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    CK(cudaDeviceSynchronize());
+    CK(debug_trace(on, out128));
+    return MATINV_OK;
+}
+
 int matinv_ffma_peak_tflops(double *tflops_out, void *stream) {
     g_err[0] = 0;
     if (!tflops_out) return fail(MATINV_E_INVALID, "invalid argument");

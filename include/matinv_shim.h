@@ -110,6 +110,10 @@ int matinv_last_timing(double *total_s, double *compute_s);
 void matinv_profile_enable(int on);
 int matinv_profile_read(double *gemm_ms, long long *gemm_launches, double *gemm_flops, long long *all_launches);
 
+/* Tuning aid: switch the in-kernel timeline of the panel kernels on/off and read the SM-clock stamps of
+ * the last launch (128 slots; see gj_subpanel.cu).  out128 may be NULL. */
+int matinv_debug_trace(int on, long long *out128);
+
 /* FFMA throughput micro-benchmark (TFLOP/s) -- the FP32 SIMT roofline denominator, measured live. */
 int matinv_ffma_peak_tflops(double *tflops_out, void *stream);
 
