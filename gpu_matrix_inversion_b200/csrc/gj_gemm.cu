@@ -9,15 +9,20 @@
 // order -- the exact FMA chain of the unblocked algorithm, hence bit-identical results and
 // bit-identical pivots downstream.  No split-K, no `a - sum`, no tensor-core reordering.
 //
-// FP32 SIMT GEMM, 128x128 CTA tile, 8x8 register tile per thread, K chunks of 16 staged in shared
-// memory by a 3-deep cp.async ring.  Operands are both K-major in HBM (CmT[t][i], U[t][j]) so the
+// FP32 SIMT GEMM, 128x128 CTA tile, 8x8 register tile per thread, K chunks staged in shared
+// memory by a cp.async ring.  Operands are both K-major in HBM (CmT[t][i], U[t][j]) so the
 // staging is a straight copy and the inner loop is 4 LDS.128 + 64 FFMA per k.
+//
+// Lane mapping (MAP = 1): measured on B200 (tools/lds_probe.cu), an LDS.128 whose equal addresses
+// sit in CONSECUTIVE lanes costs 2 cycles, the same data shared by lanes 8 apart costs 4.  Each
+// quarter-warp is therefore a 2(m) x 4(n) patch of the 4 x 8 lane grid, so both the A and the B
+// fragment loads see their duplicates inside a quarter-warp.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
-#define GT 128        // tile edge
-#define GBK 16        // k chunk
-#define GSTAGES 3
+#define GT 128  // tile edge
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -27,16 +32,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+template <int BK, int STAGES>
 struct GemmSmem {
-    float a[GSTAGES][GBK][GT];
-    float b[GSTAGES][GBK][GT];
+    float a[STAGES][BK][GT];
+    float b[STAGES][BK][GT];
 };
 
+template <int BK, int STAGES, int MAP>
 __global__ void __launch_bounds__(256, 2)
 trailing_gemm_kernel(float *__restrict__ W, long long ld, int kt, int kb, const float *__restrict__ CmT,
                      long long ldc, const float *__restrict__ U, long long ldu) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    GemmSmem &s = *reinterpret_cast<GemmSmem *>(smem_raw);
+    GemmSmem<BK, STAGES> &s = *reinterpret_cast<GemmSmem<BK, STAGES> *>(smem_raw);
 
     int tj = blockIdx.x, ti = blockIdx.y;
     tj += (tj >= kt);  // skip the panel's tile column
@@ -44,25 +51,35 @@ trailing_gemm_kernel(float *__restrict__ W, long long ld, int kt, int kb, const 
     const long long i0 = (long long)ti * GT, j0 = (long long)tj * GT;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1, lm = lane >> 3, ln = lane & 7;
+    const int wm = warp >> 1, wn = warp & 1;
+    int lm, ln;
+    if (MAP == 0) {
+        lm = lane >> 3; ln = lane & 7;
+    } else {
+        const int q = lane >> 3, r8 = lane & 7;
+        lm = (q >> 1) * 2 + (r8 >> 2);
+        ln = (q & 1) * 4 + (r8 & 3);
+    }
     const int rm = wm * 32 + lm * 4;  // thread rows: rm+{0..3}, rm+16+{0..3}
     const int cn = wn * 64 + ln * 4;  // thread cols: cn+{0..3}, cn+32+{0..3}
 
-    // ---- operand staging: 16 x 128 floats per operand per chunk = 512 float4, 2 per thread
+    // ---- operand staging: BK x 128 floats per operand per chunk, 8 rows per pass
     const int lrow = tid >> 5, lcol = (tid & 31) * 4;
     const float *ga = CmT + i0 + lcol;
     const float *gb = U + j0 + lcol;
-    const int nchunks = (kb + GBK - 1) / GBK;
+    const int nchunks = (kb + BK - 1) / BK;
     auto issue = [&](int kc) {
-        const int st = kc % GSTAGES;
-        const long long k = (long long)kc * GBK + lrow;
-        cp_async16(&s.a[st][lrow][lcol], ga + k * ldc);
-        cp_async16(&s.a[st][lrow + 8][lcol], ga + (k + 8) * ldc);
-        cp_async16(&s.b[st][lrow][lcol], gb + k * ldu);
-        cp_async16(&s.b[st][lrow + 8][lcol], gb + (k + 8) * ldu);
+        const int st = kc % STAGES;
+#pragma unroll
+        for (int pss = 0; pss < BK / 8; pss++) {
+            const int rr = lrow + 8 * pss;
+            const long long k = (long long)kc * BK + rr;
+            cp_async16(&s.a[st][rr][lcol], ga + k * ldc);
+            cp_async16(&s.b[st][rr][lcol], gb + k * ldu);
+        }
     };
 #pragma unroll
-    for (int kc = 0; kc < GSTAGES - 1; kc++) {
+    for (int kc = 0; kc < STAGES - 1; kc++) {
         if (kc < nchunks) issue(kc);
         cp_async_commit();
     }
@@ -80,15 +97,15 @@ trailing_gemm_kernel(float *__restrict__ W, long long ld, int kt, int kb, const 
     }
 
     for (int kc = 0; kc < nchunks; kc++) {
-        cp_async_wait<GSTAGES - 2>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (kc + GSTAGES - 1 < nchunks) issue(kc + GSTAGES - 1);
+        if (kc + STAGES - 1 < nchunks) issue(kc + STAGES - 1);
         cp_async_commit();
-        const int st = kc % GSTAGES;
-        const int kmax = min(GBK, kb - kc * GBK);
-        if (kmax == GBK) {
+        const int st = kc % STAGES;
+        const int kmax = min(BK, kb - kc * BK);
+        if (kmax == BK) {
 #pragma unroll
-            for (int k = 0; k < GBK; k++) {
+            for (int k = 0; k < BK; k++) {
                 const float4 a0 = *reinterpret_cast<const float4 *>(&s.a[st][k][rm]);
                 const float4 a1 = *reinterpret_cast<const float4 *>(&s.a[st][k][rm + 16]);
                 const float4 b0 = *reinterpret_cast<const float4 *>(&s.b[st][k][cn]);
@@ -125,15 +142,38 @@ trailing_gemm_kernel(float *__restrict__ W, long long ld, int kt, int kb, const 
     }
 }
 
-void launch_trailing_gemm(float *W, long long ld, int npad, int k0, int kb, const float *CmT, long long ldc,
-                          const float *U, long long ldu, cudaStream_t st) {
+template <int BK, int STAGES, int MAP>
+static void launch_variant(float *W, long long ld, int npad, int k0, int kb, const float *CmT, long long ldc,
+                           const float *U, long long ldu, cudaStream_t st) {
     static bool configured = false;
+    const int smem = (int)sizeof(GemmSmem<BK, STAGES>);
     if (!configured) {
-        cudaFuncSetAttribute(trailing_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
+        cudaFuncSetAttribute(trailing_gemm_kernel<BK, STAGES, MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
     const int nt = npad / GT;
-    if (nt <= 1) return;
     dim3 grid(nt - 1, nt - 1);
-    trailing_gemm_kernel<<<grid, 256, sizeof(GemmSmem), st>>>(W, ld, k0 / GT, kb, CmT, ldc, U, ldu);
+    trailing_gemm_kernel<BK, STAGES, MAP><<<grid, 256, smem, st>>>(W, ld, k0 / GT, kb, CmT, ldc, U, ldu);
+}
+
+// MATINV_GEMM selects a variant (tuning aid); the default is the fastest measured on B200.
+static int gemm_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MATINV_GEMM");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+void launch_trailing_gemm(float *W, long long ld, int npad, int k0, int kb, const float *CmT, long long ldc,
+                          const float *U, long long ldu, cudaStream_t st) {
+    if (npad / GT <= 1) return;
+    switch (gemm_variant()) {
+        case 0: launch_variant<16, 3, 0>(W, ld, npad, k0, kb, CmT, ldc, U, ldu, st); break;
+        case 2: launch_variant<32, 3, 1>(W, ld, npad, k0, kb, CmT, ldc, U, ldu, st); break;
+        case 3: launch_variant<16, 4, 1>(W, ld, npad, k0, kb, CmT, ldc, U, ldu, st); break;
+        case 4: launch_variant<8, 4, 1>(W, ld, npad, k0, kb, CmT, ldc, U, ldu, st); break;
+        default: launch_variant<16, 3, 1>(W, ld, npad, k0, kb, CmT, ldc, U, ldu, st); break;
+    }
 }

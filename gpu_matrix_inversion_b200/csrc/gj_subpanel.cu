@@ -47,6 +47,30 @@ __device__ __forceinline__ void st_cluster_f4(unsigned addr, const float4 &v) {
                  : "memory");
 }
 
+__device__ __forceinline__ void st_async_f4(unsigned addr, const float4 &v, unsigned mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(a), "r"(parity)
+        : "memory");
+}
+
 struct __align__(16) SubMail {  // 80 bytes = 5 float4
     u64 key;
     u64 pad;
@@ -54,12 +78,12 @@ struct __align__(16) SubMail {  // 80 bytes = 5 float4
 };
 
 struct __align__(16) SubSmem {
-    SubMail mail[2][SP_MAXCTA];  // [step parity][source CTA]  -- written remotely
-    SubMail wcand[SP_THREADS / 32];
-    float u[16];
-    int p;
-    float v;
-    int pad[2];
+    SubMail mail[2][SP_MAXCTA];       // [step parity][source CTA]  -- written remotely (st.async)
+    SubMail wcand[SP_THREADS / 32];   // staging of the CTA winner's candidate (only the winner's warp uses its slot)
+    float uw[SP_THREADS / 32][16];    // per-warp copy of the normalised pivot row (rotated)
+    u64 mbar[2];                      // one transaction barrier per step parity
+    u64 cta_key[3];                   // CTA-level arg max by shared-memory atomicMax, reset two steps ahead
+    u64 pad;
     // followed by: float hist[W][R * SP_THREADS]
 };
 
@@ -96,7 +120,14 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
         }
     }
     TRACE(rank == 0, 1);
-    // every CTA of the cluster must be resident before anyone writes into its shared memory
+    if (tid == 0) {
+        mbar_init(&s.mbar[0], 1);
+        mbar_init(&s.mbar[1], 1);
+        s.cta_key[0] = 0; s.cta_key[1] = 0; s.cta_key[2] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // every CTA of the cluster must be resident (and its barriers initialised) before anyone writes into its
+    // shared memory
     cluster_arrive();
     cluster_wait();
     TRACE(rank == 0, 2);
@@ -108,7 +139,10 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
     for (int t = 0; t < W; t++) {
         if (t < sw) {
             const int r = k0 + s0 + t;
-            // ---- (1) local candidates, warp arg max (two redux.sync: magnitude, then lowest position)
+            TRACE(rank == 0 && t == 8, 64);
+            // ---- (1) local candidates -> warp arg max (two redux.sync) -> CTA arg max (smem atomicMax)
+            const int par = t & 1;
+            if (tid == 0) mbar_expect_tx(&s.mbar[par], nct * (16 + 4 * W));
             unsigned mag = 0;
             int cand = 0x7FFFFFFF, bq = -1;
 #pragma unroll
@@ -121,72 +155,84 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
             const bool has = bq >= 0;
             const unsigned gm = __reduce_max_sync(0xffffffffu, has ? mag : 0u);
             const unsigned pw = __reduce_min_sync(0xffffffffu, (has && mag == gm) ? (unsigned)cand : 0x7FFFFFFFu);
-            if (pw == 0x7FFFFFFFu) {
-                if (lane == 0) s.wcand[warp].key = 0;
-            } else if (has && mag == gm && (unsigned)cand == pw) {  // exactly one lane: positions are distinct
-                SubMail &c = s.wcand[warp];
+            u64 mykey = 0;
+            if (has && mag == gm && (unsigned)cand == pw) {  // exactly one lane per warp: positions are distinct
+                float xv = 0.0f;
 #pragma unroll
                 for (int q = 0; q < R; q++)
-                    if (q == bq) {
-                        c.key = gj_key_from(mag, cand, x[q][0]);
-#pragma unroll
-                        for (int f = 0; f < W / 4; f++)
-                            *reinterpret_cast<float4 *>(&c.row[4 * f]) =
-                                make_float4(x[q][4 * f], x[q][4 * f + 1], x[q][4 * f + 2], x[q][4 * f + 3]);
-                    }
+                    if (q == bq) xv = x[q][0];
+                mykey = gj_key_from(mag, cand, xv);
+                atomicMax(&s.cta_key[t % 3], mykey);
             }
+            TRACE(rank == 0 && t == 8, 65);
             __syncthreads();
-            // ---- (2) warp 0: CTA best, pushed into every CTA's mailbox (DSMEM all-to-all)
-            if (warp == 0) {
-                const bool inr = lane < SP_THREADS / 32;
-                const u64 k = inr ? s.wcand[lane].key : 0;
-                const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
-                const unsigned ghi = __reduce_max_sync(0xffffffffu, hi);
-                const unsigned glo = __reduce_max_sync(0xffffffffu, (inr && hi == ghi) ? lo : 0u);
-                const unsigned hit = __ballot_sync(0xffffffffu, inr && hi == ghi && lo == glo);
-                const int wsrc = __ffs(hit) - 1;
-                const float4 *src = reinterpret_cast<const float4 *>(&s.wcand[wsrc]);
+            TRACE(rank == 0 && t == 8, 66);
+            if (tid == 0) s.cta_key[(t + 2) % 3] = 0;
+            // ---- (2) the winner's warp pushes (key, row) into every CTA's mailbox: DSMEM st.async, completion
+            //          counted by the destination's transaction barrier -- no cluster-wide barrier per step
+            const u64 ck = s.cta_key[t % 3];
+            const bool iwin = (mykey != 0) && (mykey == ck);
+            const bool nocand = (ck == 0);  // no candidate row in this CTA: warp 0 sends the empty key
+            if (__any_sync(0xffffffffu, iwin) || (nocand && warp == 0)) {
+                SubMail &c = s.wcand[warp];
+                if (iwin) {
+                    c.key = mykey;
+#pragma unroll
+                    for (int q = 0; q < R; q++)
+                        if (q == bq) {
+#pragma unroll
+                            for (int f = 0; f < W / 4; f++)
+                                *reinterpret_cast<float4 *>(&c.row[4 * f]) =
+                                    make_float4(x[q][4 * f], x[q][4 * f + 1], x[q][4 * f + 2], x[q][4 * f + 3]);
+                        }
+                } else if (nocand && lane == 0) {
+                    c.key = 0;
+                }
+                __syncwarp();
+                const float4 *src = reinterpret_cast<const float4 *>(&c);
                 const unsigned dst_cta = lane & 15;
                 if (dst_cta < nct) {
-                    const unsigned base = mapa_shared(&s.mail[t & 1][rank], dst_cta);
-                    for (int f = lane >> 4; f < 1 + W / 4; f += 2) st_cluster_f4(base + 16 * f, src[f]);
+                    const unsigned base = mapa_shared(&s.mail[par][rank], dst_cta);
+                    const unsigned rbar = mapa_shared(&s.mbar[par], dst_cta);
+                    for (int f = lane >> 4; f < 1 + W / 4; f += 2) st_async_f4(base + 16 * f, src[f], rbar);
                 }
             }
-            cluster_arrive();
-            cluster_wait();
-            // ---- (3) warp 0: cluster best -> pivot row p, value v, normalised pivot row u (rotated)
-            if (warp == 0) {
+            TRACE(rank == 0 && t == 8, 67);
+            mbar_wait(&s.mbar[par], (t >> 1) & 1);
+            TRACE(rank == 0 && t == 8, 68);
+            // ---- (3) every warp: cluster arg max -> pivot row p, value v, normalised pivot row u (rotated)
+            int p;
+            {
                 const bool inr = lane < (int)nct;
-                const u64 k = inr ? s.mail[t & 1][lane].key : 0;
+                const u64 k = inr ? s.mail[par][lane].key : 0;
                 const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
                 const unsigned ghi = __reduce_max_sync(0xffffffffu, hi);
                 const unsigned glo = __reduce_max_sync(0xffffffffu, (inr && hi == ghi) ? lo : 0u);
                 const unsigned hit = __ballot_sync(0xffffffffu, inr && hi == ghi && lo == glo);
                 const int csrc = __ffs(hit) - 1;
                 const u64 kg = ((u64)ghi << 32) | glo;
-                const int p = gj_key_row(kg);
+                p = gj_key_row(kg);
                 const float v = gj_key_value(kg);
                 if (lane < W) {
-                    const float rowv = s.mail[t & 1][csrc].row[lane];
-                    s.u[(lane + W - 1) % W] = (lane == 0) ? 1.0f / v : rowv / v;
+                    const float rowv = s.mail[par][csrc].row[lane];
+                    s.uw[warp][(lane + W - 1) % W] = (lane == 0) ? 1.0f / v : rowv / v;
                 }
-                if (lane == 0) {
-                    s.p = p;
-                    if (rank == 0) {
-                        piv[r] = p;
-                        pv[s0 + t] = v;
-                        if (gj_bad_pivot(v) && *info == 0) *info = r + 1;
-                    }
+                if (rank == 0 && tid == 0) {
+                    piv[r] = p;
+                    pv[s0 + t] = v;
+                    if (gj_bad_pivot(v) && *info == 0) *info = r + 1;
                 }
             }
-            __syncthreads();
+            __syncwarp();
+            TRACE(rank == 0 && t == 8, 69);
             float u[W];
 #pragma unroll
             for (int f = 0; f < W / 4; f++) {
-                const float4 v4 = *reinterpret_cast<const float4 *>(&s.u[4 * f]);
+                const float4 v4 = *reinterpret_cast<const float4 *>(&s.uw[warp][4 * f]);
                 u[4 * f] = v4.x; u[4 * f + 1] = v4.y; u[4 * f + 2] = v4.z; u[4 * f + 3] = v4.w;
             }
-            const int p = s.p;
+            __syncwarp();
+            TRACE(rank == 0 && t == 8, 70);
             // ---- (4) implicit swap + rank-1 update from registers; multipliers recorded in smem
 #pragma unroll
             for (int q = 0; q < R; q++) {
@@ -356,6 +402,13 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
 
     // ===== regular CTA: rows [i0, i0 + 64)
     const int i0 = blockIdx.x * MATINV_RB;
+    // my 8 rows are fetched up front: the loads fly while the permutation / recurrence prologue runs
+    float4 pre[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int i = i0 + warp * 8 + q;
+        pre[q] = (i < n) ? *reinterpret_cast<const float4 *>(in + (long long)i * ld_in + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (warp == 0) build_subperm(piv, r0, sw, s.pos, s.content, &s.m);
     for (int e = tid; e < 16 * MATINV_RB; e += 256) {
         const int t = e / MATINV_RB, ii = e - t * MATINV_RB;
@@ -413,7 +466,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
     float4 us[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) us[t] = *reinterpret_cast<const float4 *>(&s.us[t][4 * lane]);
-#pragma unroll 2
+#pragma unroll
     for (int q = 0; q < 8; q++) {
         const int ii = warp * 8 + q, i = i0 + ii;
         if (i >= n) continue;  // warp-uniform
@@ -423,7 +476,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
         } else {
             const int slot = s.rowmap[ii];
             if (slot >= 0) acc = *reinterpret_cast<const float4 *>(&s.old_[s.content[slot]][4 * lane]);
-            else acc = *reinterpret_cast<const float4 *>(in + (long long)i * ld_in + 4 * lane);
+            else acc = pre[q];
 #pragma unroll
             for (int t = 0; t < 16; t++) {
                 const float c = s.cs[t][ii];  // zero beyond sw: fma(-0, 0, a) == a
