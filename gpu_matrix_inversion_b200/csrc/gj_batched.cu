@@ -145,84 +145,100 @@ batched_reg_kernel(const float *__restrict__ A, long long batch, float *__restri
         int sinfo = 0;
         __syncwarp();
 
+        // Steps run in groups of 4 with STATIC column indices inside a group; after each group the register
+        // window rotates left by 4 (a[.][j] <- a[.][j+4]), so the loop over groups is rolled (small code) at the
+        // cost of N/4 register moves per step and row.  Window position w of group g is column 4g + w (mod N).
 #pragma unroll 1
-        for (int r = 0; r < N; r++) {
-            // ---- (1) pivot search over the not-yet-used rows (== logical positions >= r)
-            unsigned mag = 0;
-            int cand = 0x7FFFFFFF;
-            bool has = false;
+        for (int g = 0; g < N / 4; g++) {
+#pragma unroll
+            for (int tc = 0; tc < 4; tc++) {
+                const int r = 4 * g + tc;
+                // ---- (1) pivot search over the not-yet-used rows (== logical positions >= r)
+                unsigned mag = 0;
+                int cand = 0x7FFFFFFF;
+                bool has = false;
+#pragma unroll
+                for (int s = 0; s < RS; s++) {
+                    if (!used[s]) {
+                        const unsigned mq = gj_mag(a[s][tc], lpos[s] == r);
+                        if (!has || mq > mag || (mq == mag && lpos[s] < cand)) { mag = mq; cand = lpos[s]; has = true; }
+                    }
+                }
+                const unsigned gm = __reduce_max_sync(0xffffffffu, has ? mag : 0u);
+                const int p = (int)__reduce_min_sync(0xffffffffu, (has && mag == gm) ? (unsigned)cand : 0x7FFFFFFFu);
+                bool own[RS];
+#pragma unroll
+                for (int s = 0; s < RS; s++) own[s] = !used[s] && lpos[s] == p;
+                const unsigned b0 = __ballot_sync(0xffffffffu, own[0]);
+                unsigned b1 = 0;
+                if (RS > 1) b1 = __ballot_sync(0xffffffffu, own[RS - 1]);
+                const int Sp = b0 ? 0 : 1;               // warp-uniform slot of the pivot row
+                const int Lp = __ffs(b0 ? b0 : b1) - 1;  // its lane
+                const float v = __shfl_sync(0xffffffffu, (Sp == 0) ? a[0][tc] : a[RS - 1][tc], Lp);
+                if (gj_bad_pivot(v) && sinfo == 0) sinfo = r + 1;
+                // ---- (2) publish the raw pivot row (window order)
+                if (lane == Lp) {
+                    if (Sp == 0) {
+#pragma unroll
+                        for (int f = 0; f < N / 4; f++)
+                            reinterpret_cast<float4 *>(raw)[f] = make_float4(a[0][4 * f], a[0][4 * f + 1], a[0][4 * f + 2], a[0][4 * f + 3]);
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < N / 4; f++)
+                            reinterpret_cast<float4 *>(raw)[f] =
+                                make_float4(a[RS - 1][4 * f], a[RS - 1][4 * f + 1], a[RS - 1][4 * f + 2], a[RS - 1][4 * f + 3]);
+                    }
+                }
+                __syncwarp();
+                // ---- (3) true division, RS elements per lane; the pivot position receives 1/v
+#pragma unroll
+                for (int k = 0; k < RS; k++) {
+                    const int pos = lane * RS + k;
+                    const float val = raw[pos];
+                    urot[pos] = (pos == tc) ? 1.0f / v : val / v;
+                }
+                __syncwarp();
+                // ---- (4) rank-1 update; u is consumed straight from shared memory, four values at a time
+#pragma unroll
+                for (int s = 0; s < RS; s++) {
+                    if (s == Sp && lane == Lp) {
+                        // the pivot row becomes u: reloaded with LDS.128 (cheaper than N predicated moves)
+#pragma unroll
+                        for (int f = 0; f < N / 4; f++)
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(a[s][4 * f]), "=f"(a[s][4 * f + 1]), "=f"(a[s][4 * f + 2]), "=f"(a[s][4 * f + 3])
+                                         : "r"(urot_s + 16 * f));
+                    } else {
+                        const float c = a[s][tc];
+#pragma unroll
+                        for (int f = 0; f < N / 4; f++) {
+                            const float4 u4 = reinterpret_cast<const float4 *>(urot)[f];
+                            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const int j = 4 * f + k;
+                                a[s][j] = (j == tc) ? fmaf(-c, uu[k], 0.0f) : gj_elim(a[s][j], c, uu[k]);
+                            }
+                        }
+                    }
+                }
+                // ---- (5) bookkeeping: logical positions, column permutation
+#pragma unroll
+                for (int s = 0; s < RS; s++) {
+                    if (own[s]) { used[s] = true; lpos[s] = r; }
+                    else if (!used[s] && lpos[s] == r) lpos[s] = p;
+                }
+                if (lane == 0) { const int q1 = qinv[r], q2 = qinv[p]; qinv[r] = q2; qinv[p] = q1; }
+                __syncwarp();
+            }
+            // rotate the window left by 4
 #pragma unroll
             for (int s = 0; s < RS; s++) {
-                if (!used[s]) {
-                    const unsigned mq = gj_mag(a[s][0], lpos[s] == r);
-                    if (!has || mq > mag || (mq == mag && lpos[s] < cand)) { mag = mq; cand = lpos[s]; has = true; }
-                }
+                const float t0 = a[s][0], t1 = a[s][1], t2 = a[s][2], t3 = a[s][3];
+#pragma unroll
+                for (int j = 0; j < N - 4; j++) a[s][j] = a[s][j + 4];
+                a[s][N - 4] = t0; a[s][N - 3] = t1; a[s][N - 2] = t2; a[s][N - 1] = t3;
             }
-            const unsigned gm = __reduce_max_sync(0xffffffffu, has ? mag : 0u);
-            const int p = (int)__reduce_min_sync(0xffffffffu, (has && mag == gm) ? (unsigned)cand : 0x7FFFFFFFu);
-            bool own[RS];
-#pragma unroll
-            for (int s = 0; s < RS; s++) own[s] = !used[s] && lpos[s] == p;
-            const unsigned b0 = __ballot_sync(0xffffffffu, own[0]);
-            unsigned b1 = 0;
-            if (RS > 1) b1 = __ballot_sync(0xffffffffu, own[RS - 1]);
-            const int Sp = b0 ? 0 : 1;                       // warp-uniform slot of the pivot row
-            const int Lp = __ffs(b0 ? b0 : b1) - 1;          // its lane
-            const float v = __shfl_sync(0xffffffffu, (Sp == 0) ? a[0][0] : a[RS - 1][0], Lp);
-            if (gj_bad_pivot(v) && sinfo == 0) sinfo = r + 1;
-            // ---- (2) publish the raw pivot row
-            if (lane == Lp) {
-                if (Sp == 0) {
-#pragma unroll
-                    for (int f = 0; f < N / 4; f++)
-                        reinterpret_cast<float4 *>(raw)[f] = make_float4(a[0][4 * f], a[0][4 * f + 1], a[0][4 * f + 2], a[0][4 * f + 3]);
-                } else {
-#pragma unroll
-                    for (int f = 0; f < N / 4; f++)
-                        reinterpret_cast<float4 *>(raw)[f] =
-                            make_float4(a[RS - 1][4 * f], a[RS - 1][4 * f + 1], a[RS - 1][4 * f + 2], a[RS - 1][4 * f + 3]);
-                }
-            }
-            __syncwarp();
-            // ---- (3) true division, RS elements per lane, stored rotated (position j -> j-1, inverse -> N-1)
-#pragma unroll
-            for (int k = 0; k < RS; k++) {
-                const int pos = lane * RS + k;
-                const float val = raw[pos];
-                urot[(pos + N - 1) % N] = (pos == 0) ? 1.0f / v : val / v;
-            }
-            __syncwarp();
-            // ---- (4) rank-1 update with rotation
-            float u[N];
-#pragma unroll
-            for (int f = 0; f < N / 4; f++) {
-                const float4 v4 = reinterpret_cast<const float4 *>(urot)[f];
-                u[4 * f] = v4.x; u[4 * f + 1] = v4.y; u[4 * f + 2] = v4.z; u[4 * f + 3] = v4.w;
-            }
-#pragma unroll
-            for (int s = 0; s < RS; s++) {
-                if (s == Sp && lane == Lp) {
-                    // the pivot row becomes u: reloaded with LDS.128 (cheaper than N predicated moves)
-#pragma unroll
-                    for (int f = 0; f < N / 4; f++)
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(a[s][4 * f]), "=f"(a[s][4 * f + 1]), "=f"(a[s][4 * f + 2]), "=f"(a[s][4 * f + 3])
-                                     : "r"(urot_s + 16 * f));
-                } else {
-                    const float c = a[s][0];
-#pragma unroll
-                    for (int j = 0; j < N - 1; j++) a[s][j] = gj_elim(a[s][j + 1], c, u[j]);
-                    a[s][N - 1] = fmaf(-c, u[N - 1], 0.0f);
-                }
-            }
-            // ---- (5) bookkeeping: logical positions, column permutation
-#pragma unroll
-            for (int s = 0; s < RS; s++) {
-                if (own[s]) { used[s] = true; lpos[s] = r; }
-                else if (!used[s] && lpos[s] == r) lpos[s] = p;
-            }
-            if (lane == 0) { const int q1 = qinv[r], q2 = qinv[p]; qinv[r] = q2; qinv[p] = q1; }
-            __syncwarp();
         }
 
         // ---- result: X[lpos][qinv[c]] = a[.][c], staged through shared memory for coalesced stores

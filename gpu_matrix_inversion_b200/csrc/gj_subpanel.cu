@@ -132,10 +132,9 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
     cluster_wait();
     TRACE(rank == 0, 2);
 
-    // The step loop is ROLLED (one copy of the body stays in the instruction cache): after every step
-    // the register window rotates left by one column, so the current column is always x[.][0] and the
-    // freshly produced inverse column enters at x[.][W-1]; after W steps the window is back in place.
-#pragma unroll 1
+    // The step loop is fully UNROLLED: every register index (current column t) is static.  (A rolled loop with
+    // a rotating register window was tried: ptxas turns the rotation into ~300 register moves per step.)
+#pragma unroll
     for (int t = 0; t < W; t++) {
         if (t < sw) {
             const int r = k0 + s0 + t;
@@ -148,7 +147,7 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
 #pragma unroll
             for (int q = 0; q < R; q++) {
                 if (lpos[q] >= r) {
-                    const unsigned mq = gj_mag(x[q][0], lpos[q] == r);
+                    const unsigned mq = gj_mag(x[q][t], lpos[q] == r);
                     if (bq < 0 || mq > mag || (mq == mag && lpos[q] < cand)) { mag = mq; cand = lpos[q]; bq = q; }
                 }
             }
@@ -160,7 +159,7 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
                 float xv = 0.0f;
 #pragma unroll
                 for (int q = 0; q < R; q++)
-                    if (q == bq) xv = x[q][0];
+                    if (q == bq) xv = x[q][t];
                 mykey = gj_key_from(mag, cand, xv);
                 atomicMax(&s.cta_key[t % 3], mykey);
             }
@@ -215,7 +214,7 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
                 const float v = gj_key_value(kg);
                 if (lane < W) {
                     const float rowv = s.mail[par][csrc].row[lane];
-                    s.uw[warp][(lane + W - 1) % W] = (lane == 0) ? 1.0f / v : rowv / v;
+                    s.uw[warp][lane] = (lane == t) ? 1.0f / v : rowv / v;
                 }
                 if (rank == 0 && tid == 0) {
                     piv[r] = p;
@@ -244,23 +243,15 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
                     for (int j = 0; j < W; j++) x[q][j] = u[j];
                 } else {
                     if (lpos[q] == r) lpos[q] = p;
-                    c = x[q][0];
+                    c = x[q][t];
 #pragma unroll
-                    for (int j = 0; j < W - 1; j++) x[q][j] = gj_elim(x[q][j + 1], c, u[j]);
-                    x[q][W - 1] = fmaf(-c, u[W - 1], 0.0f);
+                    for (int j = 0; j < W; j++)
+                        if (j != t) x[q][j] = gj_elim(x[q][j], c, u[j]);
+                    x[q][t] = fmaf(-c, u[t], 0.0f);
                 }
                 hist[t * (R * SP_THREADS) + q * SP_THREADS + tid] = c;
             }
             TRACE(rank == 0, 3 + t);
-        } else {
-            // partial sub-panel (last panel only): pure rotation keeps the window aligned
-#pragma unroll
-            for (int q = 0; q < R; q++) {
-                const float x0 = x[q][0];
-#pragma unroll
-                for (int j = 0; j < W - 1; j++) x[q][j] = x[q][j + 1];
-                x[q][W - 1] = x0;
-            }
         }
     }
 
