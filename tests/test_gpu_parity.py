@@ -193,3 +193,17 @@ def test_n8192_size_independent_properties(m):
     rc, A2 = m.invert_dev(X)
     assert rc == m.OK
     assert float((A2 - A).abs().max() / A.abs().max()) <= 1e-3
+
+
+def test_python_driver_report_line(m, tmp_path):
+    """The PyOpenCL driver's entry point and report format (matrix_inv_pyopencl.py:15-17, 341-352)."""
+    from gpu_matrix_inversion_b200 import driver
+
+    out = tmp_path / "b200_32.txt"
+    with open(out, "w") as f:
+        for n in (10, 20, 250):
+            err = driver.matrix_inv(f, n, rng=np.random.default_rng(n))
+            assert err is not None and abs(err) < 1e-2
+    lines = out.read_text().splitlines()
+    assert [int(l.split()[0]) for l in lines] == [10, 20, 250]
+    assert all(len(l.split()) == 4 for l in lines)
