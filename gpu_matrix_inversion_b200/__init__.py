@@ -51,7 +51,7 @@ def _load() -> ctypes.CDLL:
         raise ImportError(
             f"{_SO} is missing: build the CUDA extension first (`make` or `python -c 'import __graft_entry__ as g; "
             f"g.build()'`).  There is no CPU fallback.")
-    L = ctypes.CDLL(str(_SO), mode=ctypes.RTLD_GLOBAL)
+    L = ctypes.CDLL(str(_SO))
     fp, ip, vp, dp = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)
     i, ll, ull = ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong
     L.matinv_device_count.restype = i

@@ -22,6 +22,7 @@ _SO = _HERE / "libgj_oracle.so"
 _SRC = _HERE / "gj_oracle.c"
 
 NOFMA = 1
+QUIRK = 2  # gj_aug_f32 only: the reference's pivot search as written (n % 256 == 0)
 
 SEED_UNIFORM = 0xB2000000
 SEED_DIAGDOM = 0xB2001000
