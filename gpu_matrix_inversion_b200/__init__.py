@@ -33,7 +33,8 @@ _SO = Path(__file__).resolve().parent / "libmatinv32.so"
 EXPORTS = [
     "matinv_device_count", "matinv_last_error", "matinv_shutdown", "matinv_invert_f32", "matinv_invert_f32_dev",
     "matinv_invert_batched_f32", "matinv_invert_batched_f32_dev", "matinv_shard_panel_bytes", "matinv_shard_create",
-    "matinv_shard_destroy", "matinv_shard_local", "matinv_shard_generate", "matinv_shard_factor",
+    "matinv_shard_destroy", "matinv_shard_local", "matinv_shard_set_block", "matinv_shard_get_block",
+    "matinv_shard_generate", "matinv_shard_factor",
     "matinv_shard_apply", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
     "matinv_profile_read", "matinv_debug_trace",
@@ -79,6 +80,10 @@ def _load() -> ctypes.CDLL:
     L.matinv_shard_destroy.restype = None
     L.matinv_shard_local.argtypes = [vp, ctypes.POINTER(ll), ctypes.POINTER(ll)]
     L.matinv_shard_local.restype = vp
+    L.matinv_shard_set_block.argtypes = [vp, i, vp, ll, vp]
+    L.matinv_shard_get_block.argtypes = [vp, i, vp, ll, vp]
+    L.matinv_shard_set_block.restype = i
+    L.matinv_shard_get_block.restype = i
     L.matinv_shard_generate.argtypes = [vp, ull, i, vp]
     L.matinv_shard_factor.argtypes = [vp, i, vp, vp]
     L.matinv_shard_apply.argtypes = [vp, i, vp, vp]

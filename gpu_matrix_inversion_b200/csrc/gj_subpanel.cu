@@ -542,3 +542,28 @@ void launch_panel_update(const float *in, long long ld_in, float *out, long long
     panel_update_kernel<<<nblk, 256, sizeof(UpdSmem), st>>>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv,
                                                             pv, ps, kb);
 }
+
+// Whole panel (kb <= 128 columns starting at global row/column k0) of a column view `Wv` (leading dimension ld): 8
+// x (sub-panel factor + in-panel update), ping-ponging through P0/P1.  piv is indexed by GLOBAL row (callers may pass
+// a pointer biased by -k0).  Returns the number of kernels launched.
+int launch_panel_factor(float *Wv, long long ld, int n, int k0, int kb, float *CmT, long long ldc, int *piv, float *pv,
+                        int *info, PanelState *ps, float *P0, float *P1, cudaStream_t st) {
+    float *P[2] = {P0, P1};
+    const int sub = subpanel_width(n);
+    const int ns = (kb + sub - 1) / sub;
+    for (int s = 0; s < ns; s++) {
+        const int s0 = s * sub;
+        const int sw = (kb - s0 < sub) ? kb - s0 : sub;
+        const float *in = (s == 0) ? Wv : P[(s - 1) & 1];
+        const long long ld_in = (s == 0) ? ld : MATINV_NB;
+        const bool to_w = (s == ns - 1) && ns > 1;
+        float *out = to_w ? Wv : P[s & 1];
+        const long long ld_out = to_w ? ld : MATINV_NB;
+        launch_subpanel(in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
+        launch_panel_update(in, ld_in, out, ld_out, n, k0, s0, sw, sub, CmT, ldc, piv, pv, ps, kb, st);
+    }
+    if (ns == 1)  // single sub-panel: in == out would alias in the update kernel, so it went through P[0]
+        cudaMemcpy2DAsync(Wv, ld * sizeof(float), P[0], MATINV_NB * sizeof(float), MATINV_NB * sizeof(float), n,
+                          cudaMemcpyDeviceToDevice, st);
+    return 2 * ns;
+}

@@ -35,14 +35,22 @@ void launch_panel_update(const float *in, long long ld_in, float *out, long long
                          cudaStream_t st);
 
 cudaError_t debug_trace(int on, long long *out128);
+int launch_panel_factor(float *Wv, long long ld, int n, int k0, int kb, float *CmT, long long ldc, int *piv, float *pv,
+                        int *info, PanelState *ps, float *P0, float *P1, cudaStream_t st);
 
 // ---- gj_rowblock.cu : row interchanges + row-block recurrence on all non-panel columns
 void launch_rowblock(float *W, long long ld, int ncols_pad, int k0, int kb, const float *CmT, long long ldc,
                      const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st);
 
+void launch_rowblock_ex(float *W, long long ld, int ncols_pad, int k0, int kb, int skip_tile, const float *CmT,
+                        long long ldc, const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st);
+
 // ---- gj_gemm.cu : trailing update  W[i][j] <- chain_t fma(-CmT[t][i], U[t][j], W[i][j])
 void launch_trailing_gemm(float *W, long long ld, int npad, int k0, int kb, const float *CmT, long long ldc,
                           const float *U, long long ldu, cudaStream_t st);
+
+void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int kb,
+                             const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st);
 
 // ---- gj_finish.cu : deferred column permutation + extraction + isfinite scan
 void launch_colperm_build(const int *piv, int n, int *colsrc, cudaStream_t st);

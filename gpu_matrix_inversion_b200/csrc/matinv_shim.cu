@@ -178,24 +178,7 @@ void panel_v0(Workspace &w, int n, int k0, int kb, cudaStream_t st) {
 
 // Panel factorisation v1: cluster sub-panel kernel + in-panel update (gj_subpanel.cu).
 void panel_v1(Workspace &w, int n, int k0, int kb, cudaStream_t st) {
-    const long long ld = w.npad;
-    const int sub = subpanel_width(n);
-    const int ns = (kb + sub - 1) / sub;
-    for (int s = 0; s < ns; s++) {
-        const int s0 = s * sub;
-        const int sw = (kb - s0 < sub) ? kb - s0 : sub;
-        const float *in = (s == 0) ? w.W + k0 : w.P[(s - 1) & 1];
-        const long long ld_in = (s == 0) ? ld : MATINV_NB;
-        const bool to_w = (s == ns - 1) && ns > 1;
-        float *out = to_w ? w.W + k0 : w.P[s & 1];
-        const long long ld_out = to_w ? ld : MATINV_NB;
-        launch_subpanel(in, ld_in, out, ld_out, n, k0, s0, sw, w.CmT, ld, w.piv, w.pv, w.info, st);
-        launch_panel_update(in, ld_in, out, ld_out, n, k0, s0, sw, sub, w.CmT, ld, w.piv, w.pv, w.ps, kb, st);
-        COUNT_LAUNCH(2);
-    }
-    if (ns == 1)
-        cudaMemcpy2DAsync(w.W + k0, ld * sizeof(float), w.P[0], MATINV_NB * sizeof(float), MATINV_NB * sizeof(float), n,
-                          cudaMemcpyDeviceToDevice, st);
+    COUNT_LAUNCH(launch_panel_factor(w.W + k0, w.npad, n, k0, kb, w.CmT, w.npad, w.piv, w.pv, w.info, w.ps, w.P[0], w.P[1], st));
 }
 
 bool use_panel_v1(int n) {
@@ -272,6 +255,19 @@ int ensure_hostio(size_t bytes, size_t ibytes) {
 }
 
 }  // namespace
+
+// shared with gj_sharded.cu
+int shim_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int shim_device_count() {
+    std::lock_guard<std::mutex> lk(g.mu);
+    return probe_locked();
+}
 
 extern "C" {
 

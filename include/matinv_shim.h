@@ -77,14 +77,18 @@ int matinv_shard_create(int n, int rank, int world, matinv_shard_t **out);
 void matinv_shard_destroy(matinv_shard_t *s);
 /* local storage: n_pad x local_cols floats, row-major with leading dimension local_ld */
 float *matinv_shard_local(matinv_shard_t *s, long long *local_cols, long long *local_ld);
+/* copy global column block J (n x 128, leading dimension ld, host or device memory) into / out of the shard;
+ * only valid on the owner of J */
+int matinv_shard_set_block(matinv_shard_t *s, int J, const float *src, long long ld, void *stream);
+int matinv_shard_get_block(matinv_shard_t *s, int J, float *dst, long long ld, void *stream);
 /* fill the local columns with the synthetic workload (same bits as the unsharded generator) */
 int matinv_shard_generate(matinv_shard_t *s, unsigned long long seed, int kind, void *stream);
 /* owner only: factor panel J in place and pack the message into panel_dev */
 int matinv_shard_factor(matinv_shard_t *s, int J, void *panel_dev, void *stream);
 /* every rank: apply panel J's swaps + row-block recurrence + trailing update to the local columns */
 int matinv_shard_apply(matinv_shard_t *s, int J, const void *panel_dev, void *stream);
-/* after the last block: deferred column permutation.  Produces, for local column blocks, the list
- * of source global columns (host array of local_cols ints) -- the host moves columns accordingly. */
+/* status word (0 ok / r+1 / -1) and the n pivot rows; the deferred column permutation X[:, j] = M[:, colsrc[j]]
+ * follows from piv and is applied by the host, which moves columns between shards accordingly */
 int matinv_shard_status(matinv_shard_t *s, int *info_host, int *piv_host, void *stream);
 
 /* ---- synthetic workloads and checks on the device (bench + tests; same bits as oracle/) ------
