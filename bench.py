@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--workload", default="n16384", choices=["n16384", "n4096", "batched64", "n65536"])
     ap.add_argument("--kind", default="uniform", choices=["uniform", "diagdom"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="batched64: matrices per GPU")
-    ap.add_argument("--n", type=int, default=0, help="n65536: override the order (e.g. 16384 for a quick sharded run)")
+    ap.add_argument("--order", type=int, default=0, help="n65536: override the order (e.g. 16384 for a quick sharded run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -346,7 +346,7 @@ def main():
         # ---- one matrix column-sharded over the ranks (strong scaling): owner factors -> NCCL broadcast -> all apply
         from gpu_matrix_inversion_b200.sharded import CudaShardBackend, ShardedInverter
 
-        n = args.n or 65536
+        n = args.order or 65536
         dev = torch.device("cuda", local)
         backend = CudaShardBackend(n, rank, world, dev)
         inv = ShardedInverter(backend, dist if world > 1 else None)

@@ -82,21 +82,18 @@ rowblock_kernel(float *__restrict__ W, long long ld, int k0, int kb, int skip_ti
             float xx[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) xx[j] = s.x[b0 + j][tid];
-#pragma unroll 1
+#pragma unroll
             for (int t = 0; t < 16; t++) {
                 if (t < sw) {
-                    const float u = xx[0] / s.pv[b0 + t];
+                    const float u = xx[t] / s.pv[b0 + t];
                     s.us[t][tid] = u;
                     U[(long long)(b0 + t) * ldu + j0 + tid] = u;
+                    xx[t] = u;
 #pragma unroll
-                    for (int j = 0; j < 15; j++) xx[j] = gj_elim(xx[j + 1], s.cpT[b0 + ((t + 1 + j) & 15)][b0 + t], u);
-                    xx[15] = u;
+                    for (int j = 0; j < 16; j++)
+                        if (j != t) xx[j] = gj_elim(xx[j], s.cpT[b0 + j][b0 + t], u);   // rows beyond kb: multipliers are 0
                 } else {
                     s.us[t][tid] = 0.0f;
-                    const float x0 = xx[0];
-#pragma unroll
-                    for (int j = 0; j < 15; j++) xx[j] = xx[j + 1];
-                    xx[15] = x0;
                 }
             }
 #pragma unroll

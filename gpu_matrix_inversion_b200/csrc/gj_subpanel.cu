@@ -88,14 +88,14 @@ struct __align__(16) SubSmem {
 };
 
 // ------------------------------------------------------------------------------------------ sub-panel
-template <int W, int R>
-__global__ void __launch_bounds__(SP_THREADS, 1)
+template <int W, int R, int TH>
+__global__ void __launch_bounds__(TH, 1)
 subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict__ out, long long ld_out, int n, int k0,
                 int s0, int sw, float *__restrict__ CmT, long long ldc, int *__restrict__ piv, float *__restrict__ pv,
                 int *__restrict__ info) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SubSmem &s = *reinterpret_cast<SubSmem *>(smem_raw);
-    float *hist = reinterpret_cast<float *>(smem_raw + sizeof(SubSmem));  // [W][R*SP_THREADS]
+    float *hist = reinterpret_cast<float *>(smem_raw + sizeof(SubSmem));  // [W][R*TH]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rank = cluster_ctarank(), nct = cluster_nctarank();
     const int trace_on = g_trace_on;
@@ -105,7 +105,7 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
     int lpos[R];
 #pragma unroll
     for (int q = 0; q < R; q++) {
-        const int i = (q * (int)nct + (int)rank) * SP_THREADS + tid;
+        const int i = (q * (int)nct + (int)rank) * TH + tid;
         lpos[q] = (i < n) ? i : -1;
         if (i < n) {
             const float4 *src = reinterpret_cast<const float4 *>(in + (long long)i * ld_in + s0);
@@ -249,7 +249,7 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
                         if (j != t) x[q][j] = gj_elim(x[q][j], c, u[j]);
                     x[q][t] = fmaf(-c, u[t], 0.0f);
                 }
-                hist[t * (R * SP_THREADS) + q * SP_THREADS + tid] = c;
+                hist[t * (R * TH) + q * TH + tid] = c;
             }
             TRACE(rank == 0, 3 + t);
         }
@@ -265,7 +265,7 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
         for (int f = 0; f < W / 4; f++) dst[f] = make_float4(x[q][4 * f], x[q][4 * f + 1], x[q][4 * f + 2], x[q][4 * f + 3]);
 #pragma unroll
         for (int t = 0; t < W; t++)
-            if (t < sw) CmT[(long long)(s0 + t) * ldc + i] = hist[t * (R * SP_THREADS) + q * SP_THREADS + tid];
+            if (t < sw) CmT[(long long)(s0 + t) * ldc + i] = hist[t * (R * TH) + q * TH + tid];
     }
     TRACE(rank == 0, 20);
     // nobody may exit while a peer could still write into its mailbox
@@ -425,26 +425,23 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
     }
     __syncthreads();
     TRACE(blockIdx.x == 3, 34);
-    // recurrence on the sw pivot rows, one thread per panel column.  Rolled loop + rotating register
-    // window (the current pivot row is always xx[0]), see subpanel_kernel.
+    // recurrence on the sw pivot rows, one thread per panel column; fully unrolled with static indices so that the
+    // reciprocal part of every division (it depends on pv only) is scheduled off the dependent chain
     if (tid < MATINV_NB) {
         float xx[16];
 #pragma unroll
         for (int t = 0; t < 16; t++) xx[t] = (t < sw) ? s.old_[s.content[t]][tid] : 0.0f;
-#pragma unroll 1
+#pragma unroll
         for (int t = 0; t < 16; t++) {
             if (t < sw) {
-                const float u = xx[0] / s.pv[t];
+                const float u = xx[t] / s.pv[t];
                 s.us[t][tid] = u;
+                xx[t] = u;
 #pragma unroll
-                for (int j = 0; j < 15; j++) xx[j] = gj_elim(xx[j + 1], s.cp[t][(t + 1 + j) & 15], u);
-                xx[15] = u;
+                for (int t2 = 0; t2 < 16; t2++)
+                    if (t2 != t) xx[t2] = gj_elim(xx[t2], s.cp[t][t2], u);   // cp is 0 beyond sw: exact no-op
             } else {
                 s.us[t][tid] = 0.0f;
-                const float x0 = xx[0];
-#pragma unroll
-                for (int j = 0; j < 15; j++) xx[j] = xx[j + 1];
-                xx[15] = x0;
             }
         }
 #pragma unroll
@@ -489,20 +486,20 @@ cudaError_t debug_trace(int on, long long *out128) {
 }
 
 // ------------------------------------------------------------------------------------------ launchers
-template <int W, int R>
+template <int W, int R, int TH>
 static cudaError_t launch_subpanel_t(int ncta, const float *in, long long ld_in, float *out, long long ld_out, int n,
                                      int k0, int s0, int sw, float *CmT, long long ldc, int *piv, float *pv, int *info,
                                      cudaStream_t st) {
-    const size_t smem = sizeof(SubSmem) + (size_t)W * R * SP_THREADS * sizeof(float);
+    const size_t smem = sizeof(SubSmem) + (size_t)W * R * TH * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(subpanel_kernel<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(subpanel_kernel<W, R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(subpanel_kernel<W, R, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(subpanel_kernel<W, R, TH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta);
-    cfg.blockDim = dim3(SP_THREADS);
+    cfg.blockDim = dim3(TH);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -512,22 +509,27 @@ static cudaError_t launch_subpanel_t(int ncta, const float *in, long long ld_in,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, subpanel_kernel<W, R>, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info);
+    return cudaLaunchKernelEx(&cfg, subpanel_kernel<W, R, TH>, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info);
 }
 
 int subpanel_width(int n) { return (n > 32768) ? 8 : 16; }
 bool subpanel_supported(int n) { return n <= 65536; }
 
+// Rows per cluster = ncta x TH x R.  256-thread CTAs (R rows per thread in registers) keep the per-step instruction
+// issue low -- every warp repeats the cross-CTA reduction -- and leave room for a trailing-GEMM CTA on the same SM.
 cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0,
                             int sw, float *CmT, long long ldc, int *piv, float *pv, int *info, cudaStream_t st) {
-    if (n <= 8192) {
+#define SP_ARGS in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st
+    if (n <= 4096) {
         int ncta = 1;
-        while (ncta * SP_THREADS < n) ncta *= 2;
-        return launch_subpanel_t<16, 1>(ncta, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
+        while (ncta * 256 < n) ncta *= 2;
+        return launch_subpanel_t<16, 1, 256>(ncta, SP_ARGS);
     }
-    if (n <= 16384) return launch_subpanel_t<16, 2>(16, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
-    if (n <= 32768) return launch_subpanel_t<16, 4>(16, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
-    return launch_subpanel_t<8, 8>(16, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st);
+    if (n <= 8192) return launch_subpanel_t<16, 2, 256>(16, SP_ARGS);
+    if (n <= 16384) return launch_subpanel_t<16, 4, 256>(16, SP_ARGS);
+    if (n <= 32768) return launch_subpanel_t<16, 4, 512>(16, SP_ARGS);
+    return launch_subpanel_t<8, 8, 512>(16, SP_ARGS);
+#undef SP_ARGS
 }
 
 void launch_panel_update(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0, int sw,

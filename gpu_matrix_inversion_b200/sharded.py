@@ -64,7 +64,7 @@ class CudaShardBackend:
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
     def new_msg(self):
-        return self.torch.empty(self.msg_bytes, dtype=self.torch.uint8, device=self.device)
+        return self.torch.zeros(self.msg_bytes, dtype=self.torch.uint8, device=self.device)
 
     def generate(self, seed: int, kind: str = "uniform"):
         self.m._check(self.m.lib.matinv_shard_generate(self.h, seed, 1 if kind == "diagdom" else 0, self._stream()))
