@@ -40,13 +40,14 @@ struct GemmSmem {
 
 template <int BK, int STAGES, int MAP>
 __global__ void __launch_bounds__(256, 2)
-trailing_gemm_kernel(float *__restrict__ W, long long ld, int row_skip, int col_skip, int kb, const float *__restrict__ CmT,
+trailing_gemm_kernel(float *__restrict__ W, long long ld, int row_skip, int col_skip, int col_skip_n, int kb,
+                     const float *__restrict__ CmT,
                      long long ldc, const float *__restrict__ U, long long ldu) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GemmSmem<BK, STAGES> &s = *reinterpret_cast<GemmSmem<BK, STAGES> *>(smem_raw);
 
     int tj = blockIdx.x, ti = blockIdx.y;
-    tj += (col_skip >= 0 && tj >= col_skip);  // skip the panel's tile column (absent on non-owner shards)
+    if (col_skip >= 0 && tj >= col_skip) tj += col_skip_n;  // skip the panel's tile column(s) (absent on non-owner shards)
     ti += (ti >= row_skip);  // skip the pivot rows' tile row
     const long long i0 = (long long)ti * GT, j0 = (long long)tj * GT;
 
@@ -143,7 +144,7 @@ trailing_gemm_kernel(float *__restrict__ W, long long ld, int row_skip, int col_
 }
 
 template <int BK, int STAGES, int MAP>
-static void launch_variant(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int kb,
+static void launch_variant(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n, int kb,
                            const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st) {
     static bool configured = false;
     const int smem = (int)sizeof(GemmSmem<BK, STAGES>);
@@ -151,10 +152,10 @@ static void launch_variant(float *W, long long ld, int nrow_tiles, int ncol_tile
         cudaFuncSetAttribute(trailing_gemm_kernel<BK, STAGES, MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    const int gx = ncol_tiles - (col_skip >= 0 ? 1 : 0), gy = nrow_tiles - 1;
+    const int gx = ncol_tiles - (col_skip >= 0 ? col_skip_n : 0), gy = nrow_tiles - 1;
     if (gx <= 0 || gy <= 0) return;
     dim3 grid(gx, gy);
-    trailing_gemm_kernel<BK, STAGES, MAP><<<grid, 256, smem, st>>>(W, ld, row_skip, col_skip, kb, CmT, ldc, U, ldu);
+    trailing_gemm_kernel<BK, STAGES, MAP><<<grid, 256, smem, st>>>(W, ld, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu);
 }
 
 // MATINV_GEMM selects a variant (tuning aid); the default is the fastest measured on B200.
@@ -167,21 +168,21 @@ static int gemm_variant() {
     return v;
 }
 
-// nrow_tiles x ncol_tiles tiles of 128; tile row `row_skip` (the pivot rows) and tile column `col_skip` (the panel,
+// nrow_tiles x ncol_tiles tiles of 128; tile row `row_skip` (the pivot rows) and `col_skip_n` tile columns from `col_skip` (the panel,
 // -1 when the panel lives on another shard) are left untouched.
-void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int kb,
+void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n, int kb,
                              const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st) {
     switch (gemm_variant()) {
-        case 1: launch_variant<16, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, kb, CmT, ldc, U, ldu, st); break;
-        case 2: launch_variant<32, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, kb, CmT, ldc, U, ldu, st); break;
-        case 3: launch_variant<16, 4, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, kb, CmT, ldc, U, ldu, st); break;
-        case 4: launch_variant<8, 4, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, kb, CmT, ldc, U, ldu, st); break;
-        default: launch_variant<16, 3, 0>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, kb, CmT, ldc, U, ldu, st); break;
+        case 1: launch_variant<16, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        case 2: launch_variant<32, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        case 3: launch_variant<16, 4, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        case 4: launch_variant<8, 4, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        default: launch_variant<16, 3, 0>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
     }
 }
 
 void launch_trailing_gemm(float *W, long long ld, int npad, int k0, int kb, const float *CmT, long long ldc,
                           const float *U, long long ldu, cudaStream_t st) {
     const int nt = npad / GT;
-    launch_trailing_gemm_ex(W, ld, nt, nt, k0 / GT, k0 / GT, kb, CmT, ldc, U, ldu, st);
+    launch_trailing_gemm_ex(W, ld, nt, nt, k0 / GT, k0 / GT, 1, kb, CmT, ldc, U, ldu, st);
 }

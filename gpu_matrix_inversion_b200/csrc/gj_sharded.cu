@@ -184,7 +184,7 @@ int matinv_shard_apply(matinv_shard_t *s, int J, const void *panel_dev, void *st
     if (s->lcols > 0) {
         launch_rowblock_ex(s->Wl, s->lcols, (int)s->lcols, k0, kb, skip, (const float *)(msg + m.cmt), s->npad, (const float *)(msg + m.pv),
                            (const PanelState *)(msg + m.ps), s->U, s->lcols, st);
-        launch_trailing_gemm_ex(s->Wl, s->lcols, s->npad / MATINV_NB, s->nlocal, J, skip, kb, (const float *)(msg + m.cmt), s->npad, s->U,
+        launch_trailing_gemm_ex(s->Wl, s->lcols, s->npad / MATINV_NB, s->nlocal, J, skip, 1, kb, (const float *)(msg + m.cmt), s->npad, s->U,
                                 s->lcols, st);
     }
     SCK(cudaGetLastError());

@@ -49,7 +49,7 @@ void launch_rowblock_ex(float *W, long long ld, int ncols_pad, int k0, int kb, i
 void launch_trailing_gemm(float *W, long long ld, int npad, int k0, int kb, const float *CmT, long long ldc,
                           const float *U, long long ldu, cudaStream_t st);
 
-void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int kb,
+void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n, int kb,
                              const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st);
 
 // ---- gj_finish.cu : deferred column permutation + extraction + isfinite scan

@@ -73,6 +73,9 @@ struct Workspace {
     u64 *part[2] = {nullptr, nullptr};
     int *piv = nullptr, *colsrc = nullptr, *info = nullptr;
     PanelState *ps = nullptr;
+    // second set for the look-ahead schedule: panel k+1 is factored while the trailing update of panel k runs
+    float *CmT2 = nullptr, *pv2 = nullptr;
+    PanelState *ps2 = nullptr;
 };
 
 struct Context {
@@ -86,6 +89,8 @@ struct Context {
     int *hostio_i = nullptr;
     size_t hostio_i_bytes = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t panel_stream = nullptr;  // high priority: the latency-critical panel kernels
+    cudaEvent_t ev_a = nullptr, ev_p = nullptr;
 } g;
 
 int probe_locked() {
@@ -102,6 +107,7 @@ void free_ws(Workspace &w) {
     cudaFree(w.W); cudaFree(w.CmT); cudaFree(w.U); cudaFree(w.P[0]); cudaFree(w.P[1]);
     cudaFree(w.urow); cudaFree(w.ccol); cudaFree(w.pv); cudaFree(w.part[0]); cudaFree(w.part[1]);
     cudaFree(w.piv); cudaFree(w.colsrc); cudaFree(w.info); cudaFree(w.ps);
+    cudaFree(w.CmT2); cudaFree(w.pv2); cudaFree(w.ps2);
     w = Workspace();
 }
 
@@ -125,6 +131,10 @@ int ensure_ws(int npad) {
     CK(cudaMalloc(&w.colsrc, N * sizeof(int)));
     CK(cudaMalloc(&w.info, sizeof(int)));
     CK(cudaMalloc(&w.ps, sizeof(PanelState)));
+    CK(cudaMalloc(&w.CmT2, MATINV_NB * N * sizeof(float)));
+    CK(cudaMalloc(&w.pv2, MATINV_NB * sizeof(float)));
+    CK(cudaMalloc(&w.ps2, sizeof(PanelState)));
+    CK(cudaMemset(w.CmT2, 0, MATINV_NB * N * sizeof(float)));
     CK(cudaMemset(w.CmT, 0, MATINV_NB * N * sizeof(float)));
     CK(cudaMemset(w.U, 0, MATINV_NB * N * sizeof(float)));
     CK(cudaMemset(w.P[0], 0, N * MATINV_NB * sizeof(float)));
@@ -212,6 +222,71 @@ void schedule_blocked(Workspace &w, int n, cudaStream_t st) {
     }
 }
 
+// Look-ahead schedule: after the row-block kernel of panel k, the tile column of panel k+1 is updated first
+// (GEMM_A), then panel k+1 is factored on a high-priority stream WHILE the rest of the trailing update of panel k
+// (GEMM_B) keeps the other SMs busy.  Same kernels, same FMA chains -- only the order of independent work changes.
+int ensure_lookahead() {
+    if (!g.panel_stream) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&g.panel_stream, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&g.ev_a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_p, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
+    const long long ld = w.npad;
+    const int nt = w.npad / MATINV_NB;
+    const int nblk = (n + MATINV_NB - 1) / MATINV_NB;
+    float *CmT[2] = {w.CmT, w.CmT2};
+    float *pv[2] = {w.pv, w.pv2};
+    PanelState *ps[2] = {w.ps, w.ps2};
+    cudaStream_t sp = g.panel_stream;
+    COUNT_LAUNCH(launch_panel_factor(w.W, ld, n, 0, (n < MATINV_NB) ? n : MATINV_NB, CmT[0], ld, w.piv, pv[0], w.info, ps[0],
+                                     w.P[0], w.P[1], st));
+    for (int k = 0; k < nblk; k++) {
+        const int k0 = k * MATINV_NB, b = k & 1;
+        const int kb = (n - k0 < MATINV_NB) ? n - k0 : MATINV_NB;
+        launch_rowblock(w.W, ld, w.npad, k0, kb, CmT[b], ld, pv[b], ps[b], w.U, ld, st);
+        COUNT_LAUNCH(1);
+        if (g_prof.on) cudaEventRecord(prof_event(), st);
+        if (k + 1 < nblk) {
+            const int k1 = k0 + MATINV_NB;
+            const int kb1 = (n - k1 < MATINV_NB) ? n - k1 : MATINV_NB;
+            // GEMM_A: tile column k+1 only
+            launch_trailing_gemm_ex(w.W + k1, ld, nt, 1, k, -1, 0, kb, CmT[b], ld, w.U + k1, ld, st);
+            cudaEventRecord(g.ev_a, st);
+            cudaStreamWaitEvent(sp, g.ev_a, 0);
+            COUNT_LAUNCH(launch_panel_factor(w.W + k1, ld, n, k1, kb1, CmT[b ^ 1], ld, w.piv, pv[b ^ 1], w.info, ps[b ^ 1], w.P[0],
+                                             w.P[1], sp));
+            cudaEventRecord(g.ev_p, sp);
+            // GEMM_B: every other tile column (skips k and k+1)
+            launch_trailing_gemm_ex(w.W, ld, nt, nt, k, k, 2, kb, CmT[b], ld, w.U, ld, st);
+            cudaStreamWaitEvent(st, g.ev_p, 0);
+            COUNT_LAUNCH(2);
+        } else {
+            launch_trailing_gemm_ex(w.W, ld, nt, nt, k, k, 1, kb, CmT[b], ld, w.U, ld, st);
+            COUNT_LAUNCH(1);
+        }
+        if (g_prof.on) {
+            cudaEventRecord(prof_event(), st);
+            const double m = (double)(w.npad - MATINV_NB);
+            g_prof.gemm_flops += 2.0 * m * m * kb;
+        }
+    }
+}
+
+bool use_lookahead(int n, int npad) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("MATINV_LOOKAHEAD");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode == 1 && use_panel_v1(n) && npad >= 8 * MATINV_NB;
+}
+
 int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cudaStream_t st, int flags) {
     if (flags & MATINV_FLAG_TF32X3) return fail(MATINV_E_UNSUPPORTED, "3xTF32 trailing update is not built in this round");
     const int npad = ((n + MATINV_NB - 1) / MATINV_NB) * MATINV_NB;
@@ -221,7 +296,11 @@ int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cud
     CK(cudaMemsetAsync(w.info, 0, sizeof(int), st));
     launch_load(A_dev, n, w.W, npad, npad, st);
     if (flags & MATINV_FLAG_UNBLOCKED) schedule_unblocked(w, n, st);
-    else schedule_blocked(w, n, st);
+    else if (use_lookahead(n, npad)) {
+        rc = ensure_lookahead();
+        if (rc) return rc;
+        schedule_lookahead(w, n, st);
+    } else schedule_blocked(w, n, st);
     COUNT_LAUNCH(3);
     launch_colperm_build(w.piv, n, w.colsrc, st);
     launch_extract(w.W, npad, n, w.colsrc, X_dev, w.info, !(flags & MATINV_FLAG_NOCHECK), st);
@@ -284,6 +363,11 @@ void matinv_shutdown(void) {
     free_ws(g.ws);
     cudaFree(g.hostio); g.hostio = nullptr; g.hostio_bytes = 0;
     cudaFree(g.hostio_i); g.hostio_i = nullptr; g.hostio_i_bytes = 0;
+    if (g.panel_stream) {
+        cudaEventDestroy(g.ev_a); cudaEventDestroy(g.ev_p);
+        cudaStreamDestroy(g.panel_stream);
+        g.panel_stream = nullptr;
+    }
     if (g.stream) {
         cudaEventDestroy(g.ev[0]); cudaEventDestroy(g.ev[1]);
         cudaStreamDestroy(g.stream);
