@@ -266,6 +266,152 @@ batched_reg_kernel(const float *__restrict__ A, long long batch, float *__restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2: TWO WARPS PER 64x64 MATRIX, one row per thread (64 data registers).  Same arithmetic and the same tricks as
+// v1 (implicit row interchanges, groups of 4 static steps + window rotation, incremental column permutation), but
+// a third of the registers: 5 CTAs x 128 threads per SM = 20 warps hide the per-step dependency chain
+// (arg max -> publish pivot row -> distributed division -> update) that left v1 latency-bound at 8 warps per SM.
+// The two warps of a matrix meet at a 64-thread named barrier three times per step.
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(128, 5)
+batched_row64_kernel(const float *__restrict__ A, long long batch, float *__restrict__ X, int *__restrict__ info) {
+    constexpr int N = 64, LD = N + 1;
+    constexpr int PER_PAIR = ((N * LD + N + 4 + 3) / 4) * 4;  // floats: stage (aliases raw,u) + qinv + keys
+    extern __shared__ __align__(16) float smem_f[];
+    const int pair = threadIdx.x >> 6, t64 = threadIdx.x & 63, wp = t64 >> 5, lane = threadIdx.x & 31;
+    float *stage = smem_f + pair * PER_PAIR;
+    float *raw = stage, *ub = stage + N;
+    int *qinv = reinterpret_cast<int *>(stage + N * LD);
+    u64 *keys = reinterpret_cast<u64 *>(stage + N * LD + N);   // [2], 8-byte aligned (N*LD+N = 4224 floats)
+    const unsigned ub_s = (unsigned)__cvta_generic_to_shared(ub);
+    const int bar = 1 + pair;
+
+    for (long long b = (long long)blockIdx.x * 2 + pair; b < batch; b += (long long)gridDim.x * 2) {
+        const float *Ab = A + b * (long long)(N * N);
+        float a[N];
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(Ab + t64 * N);
+#pragma unroll
+            for (int f = 0; f < N / 4; f++) {
+                const float4 v4 = src[f];
+                a[4 * f] = v4.x; a[4 * f + 1] = v4.y; a[4 * f + 2] = v4.z; a[4 * f + 3] = v4.w;
+            }
+        }
+        int lpos = t64;
+        bool used = false;
+        int sinfo = 0;
+        qinv[t64] = t64;
+        pair_barrier(bar);
+
+#pragma unroll 1
+        for (int g = 0; g < N / 4; g++) {
+#pragma unroll
+            for (int tc = 0; tc < 4; tc++) {
+                const int r = 4 * g + tc;
+                // ---- (1) arg max over the unused rows: warp redux, then the two warps exchange their keys
+                const unsigned mag = used ? 0u : gj_mag(a[tc], lpos == r);
+                const unsigned gm = __reduce_max_sync(0xffffffffu, mag);
+                const unsigned pw = __reduce_min_sync(0xffffffffu, (!used && mag == gm) ? (unsigned)lpos : 0x7FFFFFFFu);
+                if (pw == 0x7FFFFFFFu) {
+                    if (lane == 0) keys[wp] = 0;
+                } else if (!used && mag == gm && (unsigned)lpos == pw) {
+                    keys[wp] = gj_key_from(mag, lpos, a[tc]);
+                }
+                pair_barrier(bar);
+                const u64 k0 = keys[0], k1 = keys[1];
+                const u64 kb = k0 > k1 ? k0 : k1;
+                const int p = gj_key_row(kb);
+                const float v = gj_key_value(kb);
+                if (gj_bad_pivot(v) && sinfo == 0) sinfo = r + 1;
+                const bool own = !used && lpos == p;
+                // ---- (2) the owner publishes its raw row (window order)
+                if (own) {
+#pragma unroll
+                    for (int f = 0; f < N / 4; f++)
+                        reinterpret_cast<float4 *>(raw)[f] = make_float4(a[4 * f], a[4 * f + 1], a[4 * f + 2], a[4 * f + 3]);
+                }
+                pair_barrier(bar);
+                // ---- (3) true division, one element per thread; the pivot position receives 1/v
+                ub[t64] = (t64 == tc) ? 1.0f / v : raw[t64] / v;
+                pair_barrier(bar);
+                // ---- (4) rank-1 update, u consumed four values at a time
+                if (own) {
+#pragma unroll
+                    for (int f = 0; f < N / 4; f++)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(a[4 * f]), "=f"(a[4 * f + 1]), "=f"(a[4 * f + 2]), "=f"(a[4 * f + 3])
+                                     : "r"(ub_s + 16 * f));
+                    used = true;
+                    lpos = r;
+                } else {
+                    const float c = a[tc];
+#pragma unroll
+                    for (int f = 0; f < N / 4; f++) {
+                        const float4 u4 = reinterpret_cast<const float4 *>(ub)[f];
+                        const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int j = 4 * f + k;
+                            a[j] = (j == tc) ? fmaf(-c, uu[k], 0.0f) : gj_elim(a[j], c, uu[k]);
+                        }
+                    }
+                    if (!used && lpos == r) lpos = p;
+                }
+                if (t64 == 0) { const int q1 = qinv[r], q2 = qinv[p]; qinv[r] = q2; qinv[p] = q1; }
+            }
+            // rotate the window left by 4
+            {
+                const float t0 = a[0], t1 = a[1], t2 = a[2], t3 = a[3];
+#pragma unroll
+                for (int j = 0; j < N - 4; j++) a[j] = a[j + 4];
+                a[N - 4] = t0; a[N - 3] = t1; a[N - 2] = t2; a[N - 1] = t3;
+            }
+        }
+
+        // ---- result: X[lpos][qinv[c]] = a[c], staged through shared memory for coalesced stores
+        pair_barrier(bar);
+        {
+            float *row = stage + lpos * LD;
+#pragma unroll
+            for (int c = 0; c < N; c++) row[qinv[c]] = a[c];
+        }
+        pair_barrier(bar);
+        float *Xb = X + b * (long long)(N * N);
+        bool bad = false;
+#pragma unroll 4
+        for (int i = wp; i < N; i += 2) {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const float xv = stage[i * LD + lane + 32 * k];
+                bad |= !isfinite(xv);
+                Xb[i * N + lane + 32 * k] = xv;
+            }
+        }
+        const int anybad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) keys[wp] = anybad;
+        pair_barrier(bar);
+        if (t64 == 0 && info) info[b] = sinfo ? sinfo : ((keys[0] | keys[1]) ? -1 : 0);
+        pair_barrier(bar);
+    }
+}
+
+static cudaError_t launch_batched_row64(const float *A, long long batch, float *X, int *info, cudaStream_t st) {
+    constexpr int N = 64;
+    constexpr int PER_PAIR = ((N * (N + 1) + N + 4 + 3) / 4) * 4;
+    const size_t smem = 2 * PER_PAIR * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(batched_row64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    long long grid = (batch + 1) / 2;
+    const long long cap = 148ll * 5 * 16;
+    if (grid > cap) grid = cap;
+    batched_row64_kernel<<<(unsigned)grid, 128, smem, st>>>(A, batch, X, info);
+    return cudaGetLastError();
+}
+
 template <int N>
 static cudaError_t launch_batched_reg(const float *A, long long batch, float *X, int *info, cudaStream_t st) {
     constexpr int PER_WARP = ((N * (N + 1) + N + 3) / 4) * 4;
@@ -282,17 +428,19 @@ static cudaError_t launch_batched_reg(const float *A, long long batch, float *X,
     return cudaGetLastError();
 }
 
-static bool batched_use_reg() {
+// MATINV_BATCHED: 0 = shared-memory kernel (v0), 1 = one warp per matrix (v1), 2 = two warps per matrix (v2, default)
+static int batched_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char *e = getenv("MATINV_BATCHED");
-        mode = (e && e[0] == '0') ? 0 : 1;
+        mode = e ? atoi(e) : 2;
     }
-    return mode == 1;
+    return mode;
 }
 
 cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st) {
-    if (batched_use_reg()) {
+    if (batched_mode() >= 1) {
+        if (n == 64 && batched_mode() >= 2) return launch_batched_row64(A, batch, X, info, st);
         if (n == 64) return launch_batched_reg<64>(A, batch, X, info, st);
         if (n == 32) return launch_batched_reg<32>(A, batch, X, info, st);
     }
