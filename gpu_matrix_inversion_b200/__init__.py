@@ -35,7 +35,7 @@ EXPORTS = [
     "matinv_invert_batched_f32", "matinv_invert_batched_f32_dev", "matinv_shard_panel_bytes", "matinv_shard_create",
     "matinv_shard_destroy", "matinv_shard_local", "matinv_shard_set_block", "matinv_shard_get_block",
     "matinv_shard_generate", "matinv_shard_factor",
-    "matinv_shard_apply", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
+    "matinv_shard_apply", "matinv_shard_apply_ex", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
     "matinv_profile_read", "matinv_debug_trace",
 ]
@@ -87,6 +87,8 @@ def _load() -> ctypes.CDLL:
     L.matinv_shard_generate.argtypes = [vp, ull, i, vp]
     L.matinv_shard_factor.argtypes = [vp, i, vp, vp]
     L.matinv_shard_apply.argtypes = [vp, i, vp, vp]
+    L.matinv_shard_apply_ex.argtypes = [vp, i, vp, vp, i, i]
+    L.matinv_shard_apply_ex.restype = i
     L.matinv_shard_status.argtypes = [vp, ip, ip, vp]
     for name in ("matinv_invert_f32", "matinv_invert_f32_dev", "matinv_invert_batched_f32",
                  "matinv_invert_batched_f32_dev", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",

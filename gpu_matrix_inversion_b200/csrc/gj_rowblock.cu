@@ -31,13 +31,13 @@ struct __align__(16) RowblockSmem {
 };
 
 __global__ void __launch_bounds__(256, 1)
-rowblock_kernel(float *__restrict__ W, long long ld, int k0, int kb, int skip_tile, const float *__restrict__ CmT,
+rowblock_kernel(float *__restrict__ W, long long ld, int k0, int kb, int skip_tile, int skip_n, const float *__restrict__ CmT,
                 long long ldc, const float *__restrict__ pvg, const PanelState *__restrict__ ps, float *__restrict__ U,
                 long long ldu) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RowblockSmem &s = *reinterpret_cast<RowblockSmem *>(smem_raw);
     const int j0 = blockIdx.x * RBK_CW;
-    if ((int)blockIdx.x == skip_tile) return;  // the panel's own columns were handled by the panel kernels
+    if ((int)blockIdx.x >= skip_tile && (int)blockIdx.x < skip_tile + skip_n) return;  // panel columns (and look-ahead block)
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int m = ps->m;
 
@@ -133,8 +133,8 @@ rowblock_kernel(float *__restrict__ W, long long ld, int k0, int kb, int skip_ti
     }
 }
 
-// W: local column storage (ncols_pad columns); skip_tile = local tile index of the panel, -1 if it is not local.
-void launch_rowblock_ex(float *W, long long ld, int ncols_pad, int k0, int kb, int skip_tile, const float *CmT,
+// W: local column storage (ncols_pad columns); tiles [skip_tile, skip_tile + skip_n) are left alone (skip_n = 0: none).
+void launch_rowblock_ex(float *W, long long ld, int ncols_pad, int k0, int kb, int skip_tile, int skip_n, const float *CmT,
                         long long ldc, const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
@@ -142,10 +142,10 @@ void launch_rowblock_ex(float *W, long long ld, int ncols_pad, int k0, int kb, i
         configured = true;
     }
     if (ncols_pad <= 0) return;
-    rowblock_kernel<<<ncols_pad / RBK_CW, 256, sizeof(RowblockSmem), st>>>(W, ld, k0, kb, skip_tile, CmT, ldc, pv, ps, U, ldu);
+    rowblock_kernel<<<ncols_pad / RBK_CW, 256, sizeof(RowblockSmem), st>>>(W, ld, k0, kb, skip_tile, skip_n, CmT, ldc, pv, ps, U, ldu);
 }
 
 void launch_rowblock(float *W, long long ld, int ncols_pad, int k0, int kb, const float *CmT, long long ldc,
                      const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st) {
-    launch_rowblock_ex(W, ld, ncols_pad, k0, kb, k0 / RBK_CW, CmT, ldc, pv, ps, U, ldu, st);
+    launch_rowblock_ex(W, ld, ncols_pad, k0, kb, k0 / RBK_CW, 1, CmT, ldc, pv, ps, U, ldu, st);
 }

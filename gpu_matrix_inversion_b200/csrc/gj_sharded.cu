@@ -171,24 +171,48 @@ int matinv_shard_factor(matinv_shard_t *s, int J, void *panel_dev, void *stream)
     return MATINV_OK;
 }
 
-int matinv_shard_apply(matinv_shard_t *s, int J, const void *panel_dev, void *stream) {
-    if (!s || !panel_dev || J < 0 || J >= s->nblk) return shim_fail(MATINV_E_INVALID, "invalid argument");
+// mode 0: every local column; mode 1: only global block `block` (must be local); mode 2: every local column except
+// global block `block`.  Modes 1 + 2 together equal mode 0 -- they exist so the owner of the NEXT panel can update that
+// panel's columns first, factor it and broadcast it while the rest of the update is still running (look-ahead).
+int matinv_shard_apply_ex(matinv_shard_t *s, int J, const void *panel_dev, void *stream, int mode, int block) {
+    if (!s || !panel_dev || J < 0 || J >= s->nblk || mode < 0 || mode > 2) return shim_fail(MATINV_E_INVALID, "invalid argument");
+    if (mode != 0 && (block < 0 || block >= s->nblk || block % s->world != s->rank)) return shim_fail(MATINV_E_INVALID, "block %d is not local", block);
     cudaStream_t st = (cudaStream_t)stream;
     const MsgLayout m = msg_layout(s->npad);
     const char *msg = (const char *)panel_dev;
+    const float *CmT = (const float *)(msg + m.cmt), *pv = (const float *)(msg + m.pv);
+    const PanelState *ps = (const PanelState *)(msg + m.ps);
     const int k0 = J * MATINV_NB;
     const int kb = (s->n - k0 < MATINV_NB) ? s->n - k0 : MATINV_NB;
-    const int skip = (J % s->world == s->rank) ? J / s->world : -1;
-    SCK(cudaMemcpyAsync(s->piv + k0, msg + m.piv, kb * sizeof(int), cudaMemcpyDeviceToDevice, st));
-    merge_info_kernel<<<1, 1, 0, st>>>(s->info, (const int *)(msg + m.info));
+    const int own_tile = (J % s->world == s->rank) ? J / s->world : -1;   // the panel's own tile, if it lives here
+    const int nrt = s->npad / MATINV_NB;
+    if (mode != 2) {
+        SCK(cudaMemcpyAsync(s->piv + k0, msg + m.piv, kb * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        merge_info_kernel<<<1, 1, 0, st>>>(s->info, (const int *)(msg + m.info));
+    }
     if (s->lcols > 0) {
-        launch_rowblock_ex(s->Wl, s->lcols, (int)s->lcols, k0, kb, skip, (const float *)(msg + m.cmt), s->npad, (const float *)(msg + m.pv),
-                           (const PanelState *)(msg + m.ps), s->U, s->lcols, st);
-        launch_trailing_gemm_ex(s->Wl, s->lcols, s->npad / MATINV_NB, s->nlocal, J, skip, 1, kb, (const float *)(msg + m.cmt), s->npad, s->U,
-                                s->lcols, st);
+        if (mode == 1) {
+            const size_t off = (size_t)(block / s->world) * MATINV_NB;
+            launch_rowblock_ex(s->Wl + off, s->lcols, MATINV_NB, k0, kb, 0, 0, CmT, s->npad, pv, ps, s->U + off, s->lcols, st);
+            launch_trailing_gemm_ex(s->Wl + off, s->lcols, nrt, 1, J, -1, 0, kb, CmT, s->npad, s->U + off, s->lcols, st);
+        } else {
+            int skip = own_tile, skip_n = (own_tile >= 0) ? 1 : 0;
+            if (mode == 2) {
+                const int bt = block / s->world;
+                if (own_tile < 0) { skip = bt; skip_n = 1; }
+                else if (bt == own_tile + 1) skip_n = 2;          // world == 1: panel tile and look-ahead tile are neighbours
+                else return shim_fail(MATINV_E_INVALID, "look-ahead block must follow the panel");
+            }
+            launch_rowblock_ex(s->Wl, s->lcols, (int)s->lcols, k0, kb, skip, skip_n, CmT, s->npad, pv, ps, s->U, s->lcols, st);
+            launch_trailing_gemm_ex(s->Wl, s->lcols, nrt, s->nlocal, J, skip_n ? skip : -1, skip_n, kb, CmT, s->npad, s->U, s->lcols, st);
+        }
     }
     SCK(cudaGetLastError());
     return MATINV_OK;
+}
+
+int matinv_shard_apply(matinv_shard_t *s, int J, const void *panel_dev, void *stream) {
+    return matinv_shard_apply_ex(s, J, panel_dev, stream, 0, -1);
 }
 
 int matinv_shard_status(matinv_shard_t *s, int *info_host, int *piv_host, void *stream) {

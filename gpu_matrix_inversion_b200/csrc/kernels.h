@@ -42,7 +42,7 @@ int launch_panel_factor(float *Wv, long long ld, int n, int k0, int kb, float *C
 void launch_rowblock(float *W, long long ld, int ncols_pad, int k0, int kb, const float *CmT, long long ldc,
                      const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st);
 
-void launch_rowblock_ex(float *W, long long ld, int ncols_pad, int k0, int kb, int skip_tile, const float *CmT,
+void launch_rowblock_ex(float *W, long long ld, int ncols_pad, int k0, int kb, int skip_tile, int skip_n, const float *CmT,
                         long long ldc, const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st);
 
 // ---- gj_gemm.cu : trailing update  W[i][j] <- chain_t fma(-CmT[t][i], U[t][j], W[i][j])

@@ -87,6 +87,15 @@ class CudaShardBackend:
     def apply(self, J: int, msg):
         self.m._check(self.m.lib.matinv_shard_apply(self.h, J, ctypes.c_void_p(msg.data_ptr()), self._stream()))
 
+    def apply_only(self, J: int, msg, block: int):
+        """Update of panel J restricted to local block `block` (look-ahead: the next panel's columns first)."""
+        self.m._check(self.m.lib.matinv_shard_apply_ex(self.h, J, ctypes.c_void_p(msg.data_ptr()), self._stream(), 1, block))
+
+    def apply_except(self, J: int, msg, block: int):
+        self.m._check(self.m.lib.matinv_shard_apply_ex(self.h, J, ctypes.c_void_p(msg.data_ptr()), self._stream(), 2, block))
+
+    lookahead_capable = True
+
     def status(self):
         info = ctypes.c_int(0)
         piv = np.empty(self.n, dtype=np.int32)
@@ -110,8 +119,12 @@ class ShardedInverter:
         self.nblk = (self.n + BLOCK - 1) // BLOCK
         self.msg = [backend.new_msg(), backend.new_msg()]
 
-    def factorize(self):
+    def factorize(self, lookahead=None):
         """All block steps.  Returns (info, piv); the shards then hold M = inv(P A) column-wise."""
+        if lookahead is None:
+            lookahead = getattr(self.b, "lookahead_capable", False)
+        if lookahead:
+            return self._factorize_lookahead()
         for J in range(self.nblk):
             own = owner_of(J, self.world)
             msg = self.msg[J & 1]
@@ -120,6 +133,56 @@ class ShardedInverter:
             if self.dist is not None and self.world > 1:
                 self.dist.broadcast(msg, src=own)
             self.b.apply(J, msg)
+        return self.b.status()
+
+    def _factorize_lookahead(self):
+        """Same work, re-ordered: the owner of panel J+1 updates that panel's columns first, factors it on a
+        high-priority side stream and starts its broadcast while everybody (itself included) is still applying
+        panel J to the remaining columns; the receivers post the broadcast early on their side stream."""
+        import torch
+
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(priority=-1)
+        side = self._side
+        multi = self.dist is not None and self.world > 1
+        msg0 = self.msg[0]
+        if owner_of(0, self.world) == self.rank:
+            self.b.factor(0, msg0)
+        if multi:
+            self.dist.broadcast(msg0, src=owner_of(0, self.world))
+        for J in range(self.nblk):
+            msg = self.msg[J & 1]
+            nxt = J + 1
+            if nxt >= self.nblk:
+                self.b.apply(J, msg)
+                break
+            nmsg = self.msg[nxt & 1]
+            own_n = owner_of(nxt, self.world)
+            top = torch.cuda.Event()
+            top.record(main)                      # everything that read nmsg (apply of panel J-1) is before this point
+            work = None
+            if own_n == self.rank:
+                self.b.apply_only(J, msg, nxt)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    self.b.factor(nxt, nmsg)
+                    if multi:
+                        work = self.dist.broadcast(nmsg, src=own_n, async_op=True)
+                self.b.apply_except(J, msg, nxt)
+            else:
+                if multi:
+                    with torch.cuda.stream(side):
+                        side.wait_event(top)
+                        work = self.dist.broadcast(nmsg, src=own_n, async_op=True)
+                self.b.apply(J, msg)
+            if work is not None:
+                work.wait()                       # main stream waits for the broadcast (no host block)
+            done = torch.cuda.Event()
+            done.record(side)
+            main.wait_event(done)
         return self.b.status()
 
     def exchange_columns(self, piv):

@@ -87,6 +87,8 @@ int matinv_shard_generate(matinv_shard_t *s, unsigned long long seed, int kind, 
 int matinv_shard_factor(matinv_shard_t *s, int J, void *panel_dev, void *stream);
 /* every rank: apply panel J's swaps + row-block recurrence + trailing update to the local columns */
 int matinv_shard_apply(matinv_shard_t *s, int J, const void *panel_dev, void *stream);
+/* look-ahead split of the same update: mode 1 = only global block `block` (local), mode 2 = all local columns but it */
+int matinv_shard_apply_ex(matinv_shard_t *s, int J, const void *panel_dev, void *stream, int mode, int block);
 /* status word (0 ok / r+1 / -1) and the n pivot rows; the deferred column permutation X[:, j] = M[:, colsrc[j]]
  * follows from piv and is applied by the host, which moves columns between shards accordingly */
 int matinv_shard_status(matinv_shard_t *s, int *info_host, int *piv_host, void *stream);
