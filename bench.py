@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="n16384", choices=["n16384", "n4096", "batched64", "n65536"])
+    ap.add_argument("--workload", default="n16384", choices=["n16384", "n4096", "n32768", "batched64", "n65536"])
     ap.add_argument("--kind", default="uniform", choices=["uniform", "diagdom"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="batched64: matrices per GPU")
     ap.add_argument("--order", type=int, default=0, help="n65536: override the order (e.g. 16384 for a quick sharded run)")
@@ -159,7 +159,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_target = {"n16384": 16384, "n4096": 4096, "n65536": 65536, "batched64": 64}[args.workload]
+    n_target = {"n16384": 16384, "n4096": 4096, "n32768": 32768, "n65536": 65536, "batched64": 64}[args.workload]
     cores = os.cpu_count() or 1
     if args.workload == "batched64":
         B = 65536
@@ -232,8 +232,8 @@ def main():
     K, W = args.steps, max(args.warmup, 0)
     extra = {}
 
-    if args.workload in ("n16384", "n4096"):
-        n = 16384 if args.workload == "n16384" else 4096
+    if args.workload in ("n16384", "n4096", "n32768"):
+        n = {"n16384": 16384, "n4096": 4096, "n32768": 32768}[args.workload]
         seed = (SEED_UNIFORM if args.kind == "uniform" else SEED_DIAGDOM) + n + rank * 7919
         A = m.generate_dev(n, seed, args.kind)
         X = torch.empty_like(A)

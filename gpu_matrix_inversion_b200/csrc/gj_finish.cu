@@ -13,8 +13,8 @@
 
 __global__ void __launch_bounds__(256) load_kernel(const float *__restrict__ A, int n, float *__restrict__ W,
                                                    long long ld, int npad) {
-    const long long i = blockIdx.y;
-    const int j = blockIdx.x * 256 + threadIdx.x;
+    const long long i = blockIdx.x;   // rows on grid.x: grid.y is limited to 65535
+    const int j = blockIdx.y * 256 + threadIdx.x;
     if (j >= npad) return;
     W[i * ld + j] = (i < n && j < n) ? A[i * (long long)n + j] : 0.0f;
 }
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(512) extract_kernel(const float *__restrict__ 
 }
 
 void launch_load(const float *A, int n, float *W, long long ld, int npad, cudaStream_t st) {
-    dim3 grid((npad + 255) / 256, npad);
+    dim3 grid(npad, (npad + 255) / 256);
     load_kernel<<<grid, 256, 0, st>>>(A, n, W, ld, npad);
 }
 

@@ -21,8 +21,12 @@ if len(sys.argv) > 3 and sys.argv[3] == "batched":
 else:
     A = m.generate_dev(n, SEED_UNIFORM + n, "uniform")
     X = torch.empty_like(A)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(reps):
+        e0.record()
         rc, _ = m.invert_dev(A, X)
+        e1.record()
         assert rc == 0
     torch.cuda.synchronize()
-    print("ok", n)
+    ms = e0.elapsed_time(e1)
+    print("ok", n, "last ms", round(ms, 2), "TFLOP/s", round(2.0 * n ** 3 / ms / 1e9, 2))
