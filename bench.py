@@ -154,11 +154,14 @@ def cpu_baseline(n_target: int):
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (numpy.linalg.inv exactly
     as matrix_inv_numpy.py does it) on all host cores; each step one inversion of a bounded order."""
-    import numpy as np
-
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core (numpy is not imported yet)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(os.cpu_count() or 1)
+    import numpy as np
+
     n_target = {"n16384": 16384, "n4096": 4096, "n32768": 32768, "n65536": 65536, "batched64": 64}[args.workload]
     cores = os.cpu_count() or 1
     if args.workload == "batched64":
@@ -282,8 +285,13 @@ def main():
         peak = m.ffma_peak_tflops()
         gemm_ms = prof["gemm_ms"] / max(prof["gemm_launches"], 1)
         gemm_tflops = prof["gemm_flops"] / max(prof["gemm_launches"], 1) / (gemm_ms * 1e-3) / 1e12 if gemm_ms else 0.0
+        traffic = None
+        tf = ROOT / "profiles" / "r01_gemm_traffic.json"
+        if n == 16384 and tf.exists():   # DRAM bytes of one trailing-update launch, from the committed ncu --set full capture
+            traffic = json.loads(tf.read_text())["dram_bytes_total"]
         roofline = {"bound": "fp32_simt", "kernel": "trailing_gemm_kernel", "achieved": gemm_tflops, "peak": peak,
-                    "unit": "TFLOP/s", "frac": gemm_tflops / peak if peak else None, "traffic": None,
+                    "unit": "TFLOP/s", "frac": gemm_tflops / peak if peak else None, "traffic": traffic,
+                    "traffic_note": "DRAM bytes per launch (ncu, profiles/r01_gemm_traffic.json); algorithmic bytes 2.098e9",
                     "peak_source": "measured live: matinv_ffma_peak_tflops (FFMA register-tile probe); "
                                    "MEASURED_PEAKS.json has no FP32 SIMT entry",
                     "kernel_share_of_step": prof["gemm_ms"] / K / ms,
