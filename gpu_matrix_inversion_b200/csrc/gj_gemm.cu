@@ -163,7 +163,7 @@ static int gemm_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("MATINV_GEMM");
-        v = e ? atoi(e) : 0;  // 0 = straight 4x8 lane grid: fastest measured on B200 (48.8 vs 46.2 TFLOP/s remapped)
+        v = e ? atoi(e) : 2;  // 2 = BK 32, 3 stages, quarter-warp lane remap: fastest with the FFMA2 inner loop on B200
     }
     return v;
 }
@@ -173,11 +173,13 @@ static int gemm_variant() {
 void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n, int kb,
                              const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st) {
     switch (gemm_variant()) {
+        case 0: launch_variant<16, 3, 0>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
         case 1: launch_variant<16, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
-        case 2: launch_variant<32, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        case 5: launch_variant<32, 3, 0>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        case 6: launch_variant<32, 2, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
         case 3: launch_variant<16, 4, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
         case 4: launch_variant<8, 4, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
-        default: launch_variant<16, 3, 0>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        default: launch_variant<32, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
     }
 }
 
