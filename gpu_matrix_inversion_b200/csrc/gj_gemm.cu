@@ -163,7 +163,7 @@ static int gemm_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("MATINV_GEMM");
-        v = e ? atoi(e) : 2;  // 2 = BK 32, 3 stages, quarter-warp lane remap: fastest with the FFMA2 inner loop on B200
+        v = e ? atoi(e) : 5;  // 5 = BK 32, 3 stages, straight 4x8 lane grid: fastest with the FFMA2 inner loop on B200
     }
     return v;
 }
@@ -175,11 +175,11 @@ void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_ti
     switch (gemm_variant()) {
         case 0: launch_variant<16, 3, 0>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
         case 1: launch_variant<16, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
-        case 5: launch_variant<32, 3, 0>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
         case 6: launch_variant<32, 2, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
         case 3: launch_variant<16, 4, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
         case 4: launch_variant<8, 4, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
-        default: launch_variant<32, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        case 2: launch_variant<32, 3, 1>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
+        default: launch_variant<32, 3, 0>(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st); break;
     }
 }
 
