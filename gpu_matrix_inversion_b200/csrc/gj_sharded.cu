@@ -171,8 +171,8 @@ int matinv_shard_factor(matinv_shard_t *s, int J, void *panel_dev, void *stream)
     return MATINV_OK;
 }
 
-// mode 0: every local column; mode 1: only global block `block` (must be local); mode 2: every local column except
-// global block `block`.  Modes 1 + 2 together equal mode 0 -- they exist so the owner of the NEXT panel can update that
+// mode 0: every local column; mode 1: row-block step on every local column + trailing update of global block `block`
+// only (must be local); mode 2: trailing update of every local column except `block`.  Modes 1 + 2 together equal mode 0 -- they exist so the owner of the NEXT panel can update that
 // panel's columns first, factor it and broadcast it while the rest of the update is still running (look-ahead).
 int matinv_shard_apply_ex(matinv_shard_t *s, int J, const void *panel_dev, void *stream, int mode, int block) {
     if (!s || !panel_dev || J < 0 || J >= s->nblk || mode < 0 || mode > 2) return shim_fail(MATINV_E_INVALID, "invalid argument");
@@ -191,19 +191,21 @@ int matinv_shard_apply_ex(matinv_shard_t *s, int J, const void *panel_dev, void 
         merge_info_kernel<<<1, 1, 0, st>>>(s->info, (const int *)(msg + m.info));
     }
     if (s->lcols > 0) {
+        // row interchanges + recurrence always run on ALL local columns in the first call of a step (mode 0 / 1): the
+        // look-ahead split only divides the trailing GEMM (block first, the rest while the next panel is factored)
+        int skip = own_tile, skip_n = (own_tile >= 0) ? 1 : 0;
+        if (mode != 2)
+            launch_rowblock_ex(s->Wl, s->lcols, (int)s->lcols, k0, kb, skip, skip_n, CmT, s->npad, pv, ps, s->U, s->lcols, st);
         if (mode == 1) {
             const size_t off = (size_t)(block / s->world) * MATINV_NB;
-            launch_rowblock_ex(s->Wl + off, s->lcols, MATINV_NB, k0, kb, 0, 0, CmT, s->npad, pv, ps, s->U + off, s->lcols, st);
             launch_trailing_gemm_ex(s->Wl + off, s->lcols, nrt, 1, J, -1, 0, kb, CmT, s->npad, s->U + off, s->lcols, st);
         } else {
-            int skip = own_tile, skip_n = (own_tile >= 0) ? 1 : 0;
             if (mode == 2) {
                 const int bt = block / s->world;
                 if (own_tile < 0) { skip = bt; skip_n = 1; }
                 else if (bt == own_tile + 1) skip_n = 2;          // world == 1: panel tile and look-ahead tile are neighbours
                 else return shim_fail(MATINV_E_INVALID, "look-ahead block must follow the panel");
             }
-            launch_rowblock_ex(s->Wl, s->lcols, (int)s->lcols, k0, kb, skip, skip_n, CmT, s->npad, pv, ps, s->U, s->lcols, st);
             launch_trailing_gemm_ex(s->Wl, s->lcols, nrt, s->nlocal, J, skip_n ? skip : -1, skip_n, kb, CmT, s->npad, s->U, s->lcols, st);
         }
     }
