@@ -124,10 +124,8 @@ class ShardedInverter:
         if lookahead is None:
             import os
 
-            # measured on B200: +5 % at n = 32768, but -18 % at n = 65536, where the tall panel is factored in 8-wide
-            # sub-panels (32 high-priority launches per panel interleave badly with the trailing GEMM)
-            default = "1" if self.n <= 32768 else "0"
-            lookahead = getattr(self.b, "lookahead_capable", False) and os.environ.get("MATINV_SHARD_LOOKAHEAD", default) != "0"
+            # measured on one B200 (world = 1): 11.99 s -> 11.11 s at n = 65536, 1636 -> 1558 ms at n = 32768
+            lookahead = getattr(self.b, "lookahead_capable", False) and os.environ.get("MATINV_SHARD_LOOKAHEAD", "1") != "0"
         if lookahead:
             return self._factorize_lookahead()
         for J in range(self.nblk):
