@@ -215,7 +215,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # high-priority NCCL streams: with look-ahead the panel broadcast must not queue behind the trailing GEMM
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 
     def barrier():
         if world > 1:
