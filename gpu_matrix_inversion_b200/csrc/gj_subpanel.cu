@@ -287,35 +287,42 @@ struct __align__(16) UpdSmem {
     int rowmap[MATINV_RB];       // my row -> slot in pos[] or -1
 };
 
-// Net permutation of the sub-panel's sw swaps: pos[idx] = row of slot idx (first sw slots are the
-// pivot rows), content[idx] = slot whose ORIGINAL data ends up in slot idx.  One warp.
+// Net permutation of the sub-panel's sw (<= 16) row interchanges, one warp, no serial search: every lane tracks ONE
+// row through the sw transpositions.  Slots 0..15 are the pivot rows r0+t, slots 16..31 the distinct outside rows
+// that were picked as pivots (slot 16+t = p_t at its first occurrence).  Output, 32 entries each:
+//   pos[idx]     row of slot idx, -1 if the slot is unused
+//   content[idx] slot whose ORIGINAL data ends up in slot idx
 __device__ __forceinline__ void build_subperm(const int *__restrict__ piv, int r0, int sw, int *pos, int *content, int *mout) {
     const int lane = threadIdx.x & 31;
-    pos[lane] = (lane < sw) ? r0 + lane : -1;
-    content[lane] = lane;
-    __syncwarp();
-    int m = sw;
-    const int pl = (lane < sw) ? piv[r0 + lane] : 0;  // one coalesced read instead of sw dependent ones
+    const int pl = (lane < sw) ? piv[r0 + lane] : -1;     // p_t for t = lane (one coalesced read)
+    // all 32 lanes execute the collectives; lanes < 16 carry unique dummy keys through match_any
+    const int cand = __shfl_sync(0xffffffffu, pl, (lane - 16) & 31);
+    const bool outside = lane >= 16 && cand >= r0 + sw;
+    const unsigned grp = __match_any_sync(0xffffffffu, outside ? cand : -1 - lane);
+    int row;
+    if (lane < 16) row = (lane < sw) ? r0 + lane : -1;
+    else row = (outside && lane == __ffs(grp) - 1) ? cand : -1;
+    int where = row;                                       // where this slot's original data currently sits
     for (int t = 0; t < sw; t++) {
-        const int p = __shfl_sync(0xffffffffu, pl, t);
-        if (p == r0 + t) continue;
-        int b;
-        if (p < r0 + sw) b = p - r0;
-        else {
-            const bool hit = (lane >= sw) && (lane < m) && (pos[lane] == p);
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (bal) b = __ffs(bal) - 1;
-            else {
-                b = m;
-                if (lane == 0) pos[m] = p;
-                m++;
-            }
+        const int pt = __shfl_sync(0xffffffffu, pl, t), rt = r0 + t;
+        if (where >= 0 && pt != rt) {
+            if (where == rt) where = pt;
+            else if (where == pt) where = rt;
         }
-        __syncwarp();
-        if (lane == 0) { const int ca = content[t], cb = content[b]; content[t] = cb; content[b] = ca; }
-        __syncwarp();
     }
-    if (lane == 0) *mout = m;
+    pos[lane] = row;
+    __syncwarp();
+    if (row >= 0) {   // my data ends in the slot whose row is `where`
+        int k = -1;
+        if (where < r0 + sw) k = where - r0;
+        else {
+            for (int q = 16; q < 32; q++)
+                if (pos[q] == where) k = q;
+        }
+        content[k] = lane;
+    }
+    __syncwarp();
+    if (lane == 0) *mout = 32;
 }
 
 __global__ void __launch_bounds__(256)
@@ -379,13 +386,13 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
         // multipliers recorded by the earlier sub-panels of this panel follow their rows
         for (int e = tid; e < m * s0; e += 256) {
             const int idx = e / s0, q = e - idx * s0;
-            oldh[idx * s0 + q] = CmT[(long long)q * ldc + spos[idx]];
+            if (spos[idx] >= 0) oldh[idx * s0 + q] = CmT[(long long)q * ldc + spos[idx]];
         }
         __syncthreads();
         for (int e = tid; e < m * s0; e += 256) {
             const int idx = e / s0, q = e - idx * s0;
             const int c = scontent[idx];
-            if (c != idx) CmT[(long long)q * ldc + spos[idx]] = oldh[c * s0 + q];
+            if (spos[idx] >= 0 && c != idx) CmT[(long long)q * ldc + spos[idx]] = oldh[c * s0 + q];
         }
         TRACE(true, 50);
         return;
@@ -414,14 +421,15 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
     __syncthreads();
     TRACE(blockIdx.x == 3, 33);
     const int m = s.m;
-    if (tid < m) {
+    if (tid < m && s.pos[tid] >= 0) {
         const int ii = s.pos[tid] - i0;
         if (ii >= 0 && ii < MATINV_RB) s.rowmap[ii] = tid;
     }
     for (int e = tid; e < m * 32; e += 256) {
         const int idx = e >> 5, f = e & 31;
-        *reinterpret_cast<float4 *>(&s.old_[idx][4 * f]) =
-            *reinterpret_cast<const float4 *>(in + (long long)s.pos[idx] * ld_in + 4 * f);
+        if (s.pos[idx] >= 0)
+            *reinterpret_cast<float4 *>(&s.old_[idx][4 * f]) =
+                *reinterpret_cast<const float4 *>(in + (long long)s.pos[idx] * ld_in + 4 * f);
     }
     __syncthreads();
     TRACE(blockIdx.x == 3, 34);

@@ -207,3 +207,34 @@ def test_python_driver_report_line(m, tmp_path):
     lines = out.read_text().splitlines()
     assert [int(l.split()[0]) for l in lines] == [10, 20, 250]
     assert all(len(l.split()) == 4 for l in lines)
+
+
+def test_ragged_large_order_properties(m):
+    """N not a multiple of the 128-wide tile and larger than what the oracle finishes quickly: residual gate,
+    blocked == unblocked-schedule pivots on a leading sample, in-place call."""
+    import torch
+
+    n = 4100
+    A = m.generate_dev(n, o.SEED_UNIFORM + n, "uniform")
+    piv = torch.empty(n, dtype=torch.int32, device="cuda")
+    rc, X = m.invert_dev(A, piv=piv)
+    assert rc == m.OK
+    res, _ = m.residual_dev(A, X)
+    assert res <= 1e-5
+    Ah = A.cpu().numpy()
+    Xo, po, io = o.invert_inplace(Ah)
+    assert io == 0 and np.array_equal(piv.cpu().numpy(), po)
+    assert np.array_equal(bits(X.cpu().numpy()), bits(Xo))
+
+
+def test_device_entry_on_a_side_stream(m):
+    import torch
+
+    n = 700
+    A = torch.from_numpy(o.diagdom(n)).cuda()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        rc, X = m.invert_dev(A)
+    s.synchronize()
+    assert rc == m.OK
+    assert np.array_equal(bits(X.cpu().numpy()), bits(o.invert_inplace(o.diagdom(n))[0]))
