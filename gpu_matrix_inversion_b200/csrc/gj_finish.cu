@@ -39,9 +39,9 @@ __global__ void __launch_bounds__(256) colperm_kernel(const int *__restrict__ pi
 // coalesced.  Falls back to a direct gather when the row does not fit (n > 48K).
 __global__ void __launch_bounds__(512) extract_kernel(const float *__restrict__ W, long long ld, int n,
                                                       const int *__restrict__ colsrc, float *__restrict__ X,
-                                                      int *__restrict__ info, int check, int staged) {
+                                                      int *__restrict__ info, int check, int staged, int row0) {
     extern __shared__ float srow[];
-    const long long i = blockIdx.x;
+    const long long i = (long long)blockIdx.x + row0;
     const float *wr = W + i * ld;
     float *xr = X + i * (long long)n;
     bool bad = false;
@@ -72,8 +72,9 @@ void launch_colperm_build(const int *piv, int n, int *colsrc, cudaStream_t st) {
     colperm_kernel<<<(n + 255) / 256, 256, 0, st>>>(piv, n, colsrc);
 }
 
-void launch_extract(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check,
-                    cudaStream_t st) {
+// rows [row0, row0 + nrows) of X (X points at the full n x n output)
+void launch_extract_rows(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check, int row0,
+                         int nrows, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -81,5 +82,10 @@ void launch_extract(const float *W, long long ld, int n, const int *colsrc, floa
     }
     const size_t bytes = (size_t)n * sizeof(float);
     const int staged = bytes <= 200 * 1024;
-    extract_kernel<<<n, 512, staged ? bytes : 0, st>>>(W, ld, n, colsrc, X, info, check, staged);
+    extract_kernel<<<nrows, 512, staged ? bytes : 0, st>>>(W, ld, n, colsrc, X, info, check, staged, row0);
+}
+
+void launch_extract(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check,
+                    cudaStream_t st) {
+    launch_extract_rows(W, ld, n, colsrc, X, info, check, 0, n, st);
 }

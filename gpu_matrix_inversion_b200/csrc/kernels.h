@@ -56,6 +56,8 @@ void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_ti
 void launch_colperm_build(const int *piv, int n, int *colsrc, cudaStream_t st);
 void launch_extract(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check,
                     cudaStream_t st);
+void launch_extract_rows(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check, int row0,
+                         int nrows, cudaStream_t st);
 void launch_load(const float *A, int n, float *W, long long ld, int npad, cudaStream_t st);
 
 // ---- gj_batched.cu : n <= 128, one CTA per matrix

@@ -89,6 +89,8 @@ struct Context {
     int *hostio_i = nullptr;
     size_t hostio_i_bytes = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;   // D2H of finished row chunks, overlapped with the extraction of the next chunk
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     cudaStream_t panel_stream = nullptr;  // high priority: the latency-critical panel kernels
     cudaEvent_t ev_a = nullptr, ev_p = nullptr;
 } g;
@@ -140,6 +142,15 @@ int ensure_ws(int npad) {
     CK(cudaMemset(w.P[0], 0, N * MATINV_NB * sizeof(float)));
     CK(cudaMemset(w.P[1], 0, N * MATINV_NB * sizeof(float)));
     w.npad = npad;
+    return 0;
+}
+
+int ensure_copy_stream() {
+    if (!g.copy_stream) {
+        CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&g.ev_chunk[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_chunk[1], cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -287,7 +298,8 @@ bool use_lookahead(int n, int npad) {
     return mode == 1 && use_panel_v1(n) && npad >= 8 * MATINV_NB;
 }
 
-int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cudaStream_t st, int flags) {
+// load + factorisation + column gather list; leaves M = inv(P A) in the workspace
+int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags) {
     if (flags & MATINV_FLAG_TF32X3) return fail(MATINV_E_UNSUPPORTED, "3xTF32 trailing update is not built in this round");
     const int npad = ((n + MATINV_NB - 1) / MATINV_NB) * MATINV_NB;
     int rc = ensure_ws(npad);
@@ -303,11 +315,13 @@ int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cud
     } else schedule_blocked(w, n, st);
     COUNT_LAUNCH(3);
     launch_colperm_build(w.piv, n, w.colsrc, st);
-    launch_extract(w.W, npad, n, w.colsrc, X_dev, w.info, !(flags & MATINV_FLAG_NOCHECK), st);
-    if (piv_dev) CK(cudaMemcpyAsync(piv_dev, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
+    return 0;
+}
+
+int status_locked(cudaStream_t st) {
     int info = 0;
-    CK(cudaMemcpyAsync(&info, w.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&info, g.ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (info != 0) {
         if (info > 0) snprintf(g_err, sizeof(g_err), "singular: zero or non-finite pivot at column %d", info - 1);
@@ -315,6 +329,16 @@ int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cud
         return MATINV_SINGULAR;
     }
     return MATINV_OK;
+}
+
+int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cudaStream_t st, int flags) {
+    int rc = factor_locked(A_dev, n, st, flags);
+    if (rc) return rc;
+    Workspace &w = g.ws;
+    launch_extract(w.W, w.npad, n, w.colsrc, X_dev, w.info, !(flags & MATINV_FLAG_NOCHECK), st);
+    if (piv_dev) CK(cudaMemcpyAsync(piv_dev, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    return status_locked(st);
 }
 
 int ensure_hostio(size_t bytes, size_t ibytes) {
@@ -363,6 +387,11 @@ void matinv_shutdown(void) {
     free_ws(g.ws);
     cudaFree(g.hostio); g.hostio = nullptr; g.hostio_bytes = 0;
     cudaFree(g.hostio_i); g.hostio_i = nullptr; g.hostio_i_bytes = 0;
+    if (g.copy_stream) {
+        cudaEventDestroy(g.ev_chunk[0]); cudaEventDestroy(g.ev_chunk[1]);
+        cudaStreamDestroy(g.copy_stream);
+        g.copy_stream = nullptr;
+    }
     if (g.panel_stream) {
         cudaEventDestroy(g.ev_a); cudaEventDestroy(g.ev_p);
         cudaStreamDestroy(g.panel_stream);
@@ -398,12 +427,31 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
     cudaStream_t st = g.stream;
     CK(cudaMemcpyAsync(g.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(g.ev[0], st));
-    rc = invert_dev_locked(g.hostio, n, g.hostio, piv_host ? g.hostio_i : nullptr, st, flags);
+    rc = factor_locked(g.hostio, n, st, flags);
+    if (rc) return rc;
+    // extraction (deferred column permutation + isfinite scan) in row chunks, each chunk's D2H copy overlapped with the
+    // extraction of the next one on a second stream -- replaces getInvertedMatrix + enqueueReadBuffer (LIB:369-381)
+    rc = ensure_copy_stream();
+    if (rc) return rc;
+    {
+        Workspace &w = g.ws;
+        const int chunk = (n >= 4096) ? ((n + 15) / 16) : n;
+        int ce = 0;
+        for (int row0 = 0; row0 < n; row0 += chunk, ce ^= 1) {
+            const int nrows = (n - row0 < chunk) ? n - row0 : chunk;
+            launch_extract_rows(w.W, w.npad, n, w.colsrc, g.hostio, w.info, !(flags & MATINV_FLAG_NOCHECK), row0, nrows, st);
+            COUNT_LAUNCH(1);
+            CK(cudaEventRecord(g.ev_chunk[ce], st));
+            CK(cudaStreamWaitEvent(g.copy_stream, g.ev_chunk[ce], 0));
+            CK(cudaMemcpyAsync(X_host + (size_t)row0 * n, g.hostio + (size_t)row0 * n, (size_t)nrows * n * sizeof(float),
+                               cudaMemcpyDeviceToHost, g.copy_stream));
+        }
+        CK(cudaEventRecord(g.ev[1], st));
+        if (piv_host) CK(cudaMemcpyAsync(piv_host, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    rc = status_locked(st);
     if (rc < 0) return rc;
-    CK(cudaEventRecord(g.ev[1], st));
-    if (rc == MATINV_OK) CK(cudaMemcpyAsync(X_host, g.hostio, bytes, cudaMemcpyDeviceToHost, st));
-    if (piv_host) CK(cudaMemcpyAsync(piv_host, g.hostio_i, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(g.copy_stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
     g_t_compute = ms * 1e-3;
