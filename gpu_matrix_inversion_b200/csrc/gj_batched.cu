@@ -406,10 +406,9 @@ static cudaError_t launch_batched_row64(const float *A, long long batch, float *
     constexpr int N = 64;
     constexpr int PER_PAIR = ((N * (N + 1) + N + 4 + 3) / 4) * 4;
     const size_t smem = 2 * PER_PAIR * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(batched_row64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
     }
     long long grid = (batch + 1) / 2;
     const long long cap = 148ll * 5 * 16;
@@ -422,10 +421,9 @@ template <int N>
 static cudaError_t launch_batched_reg(const float *A, long long batch, float *X, int *info, cudaStream_t st) {
     constexpr int PER_WARP = ((N * (N + 1) + N + 3) / 4) * 4;
     const size_t smem = 4 * PER_WARP * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(batched_reg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
     }
     long long grid = (batch + 3) / 4;
     const long long cap = 148ll * 2 * 16;
@@ -451,10 +449,9 @@ cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int
         if (n == 32) return launch_batched_reg<32>(A, batch, X, info, st);
     }
     const size_t smem = ((size_t)n * (n + 1) + 3 * (size_t)n) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(batched_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 4 + 3 * 128 * 4);
-        configured = true;
     }
     long long grid = batch;
     if (grid > (1ll << 20)) grid = 1ll << 20;

@@ -75,10 +75,9 @@ void launch_colperm_build(const int *piv, int n, int *colsrc, cudaStream_t st) {
 // rows [row0, row0 + nrows) of X (X points at the full n x n output)
 void launch_extract_rows(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check, int row0,
                          int nrows, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
     }
     const size_t bytes = (size_t)n * sizeof(float);
     const int staged = bytes <= 200 * 1024;

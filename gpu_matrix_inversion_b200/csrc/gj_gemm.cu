@@ -146,11 +146,10 @@ trailing_gemm_kernel(float *__restrict__ W, long long ld, int row_skip, int col_
 template <int BK, int STAGES, int MAP>
 static void launch_variant(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n, int kb,
                            const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured[64] = {};
     const int smem = (int)sizeof(GemmSmem<BK, STAGES>);
-    if (!configured) {
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(trailing_gemm_kernel<BK, STAGES, MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
     }
     const int gx = ncol_tiles - (col_skip >= 0 ? col_skip_n : 0), gy = nrow_tiles - 1;
     if (gx <= 0 || gy <= 0) return;

@@ -136,10 +136,9 @@ rowblock_kernel(float *__restrict__ W, long long ld, int k0, int kb, int skip_ti
 // W: local column storage (ncols_pad columns); tiles [skip_tile, skip_tile + skip_n) are left alone (skip_n = 0: none).
 void launch_rowblock_ex(float *W, long long ld, int ncols_pad, int k0, int kb, int skip_tile, int skip_n, const float *CmT,
                         long long ldc, const float *pv, const PanelState *ps, float *U, long long ldu, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(rowblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowblockSmem));
-        configured = true;
     }
     if (ncols_pad <= 0) return;
     rowblock_kernel<<<ncols_pad / RBK_CW, 256, sizeof(RowblockSmem), st>>>(W, ld, k0, kb, skip_tile, skip_n, CmT, ldc, pv, ps, U, ldu);

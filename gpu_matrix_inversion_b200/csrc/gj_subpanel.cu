@@ -499,11 +499,10 @@ static cudaError_t launch_subpanel_t(int ncta, const float *in, long long ld_in,
                                      int k0, int s0, int sw, float *CmT, long long ldc, int *piv, float *pv, int *info,
                                      cudaStream_t st) {
     const size_t smem = sizeof(SubSmem) + (size_t)W * R * TH * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(subpanel_kernel<W, R, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(subpanel_kernel<W, R, TH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        configured = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta);
@@ -542,10 +541,9 @@ cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long l
 void launch_panel_update(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0, int sw,
                          int wfull, float *CmT, long long ldc, const int *piv, const float *pv, PanelState *ps, int kb,
                          cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem));
-        configured = true;
     }
     const int nblk = (n + MATINV_RB - 1) / MATINV_RB + 1;
     panel_update_kernel<<<nblk, 256, sizeof(UpdSmem), st>>>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv,

@@ -6,6 +6,16 @@
 
 typedef unsigned long long u64;
 
+// cudaFuncSetAttribute is per device: launchers configure their kernel once on every device they are used on
+inline bool first_use_on_device(bool (&flags)[64]) {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (flags[d]) return false;
+    flags[d] = true;
+    return true;
+}
+
 // Per-panel bookkeeping living in device memory (written by kernels, never by the host).
 struct PanelState {
     int pos[2 * 128];      // row index of every slot touched by this panel's swaps (first kb = pivot rows)

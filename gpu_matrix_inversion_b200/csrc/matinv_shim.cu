@@ -82,6 +82,7 @@ struct Context {
     std::mutex mu;
     bool probed = false;
     int ndev = 0;
+    int device = -1;  // device the cached workspace / streams live on
     Workspace ws;
     cudaStream_t stream = nullptr;
     float *hostio = nullptr;  // device staging for the host-pointer entries
@@ -95,12 +96,26 @@ struct Context {
     cudaEvent_t ev_a = nullptr, ev_p = nullptr;
 } g;
 
+void release_locked();
+
+// Device count; also rebinds the cached workspace and streams when the caller has switched the current
+// device since the last call (everything cached belongs to exactly one device).
 int probe_locked() {
     if (!g.probed) {
         int n = 0;
         if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; cudaGetLastError(); }
         g.ndev = n;
         g.probed = true;
+    }
+    if (g.ndev > 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (g.device >= 0 && g.device != cur) {
+            cudaSetDevice(g.device);
+            release_locked();
+            cudaSetDevice(cur);
+        }
+        g.device = cur;
     }
     return g.ndev;
 }
@@ -111,6 +126,27 @@ void free_ws(Workspace &w) {
     cudaFree(w.piv); cudaFree(w.colsrc); cudaFree(w.info); cudaFree(w.ps);
     cudaFree(w.CmT2); cudaFree(w.pv2); cudaFree(w.ps2);
     w = Workspace();
+}
+
+void release_locked() {
+    free_ws(g.ws);
+    cudaFree(g.hostio); g.hostio = nullptr; g.hostio_bytes = 0;
+    cudaFree(g.hostio_i); g.hostio_i = nullptr; g.hostio_i_bytes = 0;
+    if (g.copy_stream) {
+        cudaEventDestroy(g.ev_chunk[0]); cudaEventDestroy(g.ev_chunk[1]);
+        cudaStreamDestroy(g.copy_stream);
+        g.copy_stream = nullptr;
+    }
+    if (g.panel_stream) {
+        cudaEventDestroy(g.ev_a); cudaEventDestroy(g.ev_p);
+        cudaStreamDestroy(g.panel_stream);
+        g.panel_stream = nullptr;
+    }
+    if (g.stream) {
+        cudaEventDestroy(g.ev[0]); cudaEventDestroy(g.ev[1]);
+        cudaStreamDestroy(g.stream);
+        g.stream = nullptr;
+    }
 }
 
 int ensure_ws(int npad) {
@@ -383,25 +419,13 @@ const char *matinv_last_error(void) { return g_err; }
 
 void matinv_shutdown(void) {
     std::lock_guard<std::mutex> lk(g.mu);
-    if (!g.probed || g.ndev == 0) return;
-    free_ws(g.ws);
-    cudaFree(g.hostio); g.hostio = nullptr; g.hostio_bytes = 0;
-    cudaFree(g.hostio_i); g.hostio_i = nullptr; g.hostio_i_bytes = 0;
-    if (g.copy_stream) {
-        cudaEventDestroy(g.ev_chunk[0]); cudaEventDestroy(g.ev_chunk[1]);
-        cudaStreamDestroy(g.copy_stream);
-        g.copy_stream = nullptr;
-    }
-    if (g.panel_stream) {
-        cudaEventDestroy(g.ev_a); cudaEventDestroy(g.ev_p);
-        cudaStreamDestroy(g.panel_stream);
-        g.panel_stream = nullptr;
-    }
-    if (g.stream) {
-        cudaEventDestroy(g.ev[0]); cudaEventDestroy(g.ev[1]);
-        cudaStreamDestroy(g.stream);
-        g.stream = nullptr;
-    }
+    if (!g.probed || g.ndev == 0 || g.device < 0) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != g.device) cudaSetDevice(g.device);
+    release_locked();
+    if (cur != g.device) cudaSetDevice(cur);
+    g.device = -1;
 }
 
 int matinv_invert_f32_dev(const float *A_dev, int n, float *X_dev, int *piv_dev, void *stream, int flags) {
