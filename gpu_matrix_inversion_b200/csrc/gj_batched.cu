@@ -432,19 +432,22 @@ static cudaError_t launch_batched_reg(const float *A, long long batch, float *X,
     return cudaGetLastError();
 }
 
-// MATINV_BATCHED: 0 = shared-memory kernel (v0), 1 = one warp per matrix (v1, default), 2 = two warps per matrix (v2)
+// MATINV_BATCHED: 0 = shared-memory kernel (v0), 1 = one warp per matrix, scalar FMAs (v1), 2 = two warps per matrix (v2),
+// 3 = one warp per matrix on packed pairs, gj_batched_pk.cu (v3, default: 2.50e7 inversions/s on B200 against 2.19e7 for
+// v1 and 1.7e7 for v2)
 static int batched_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char *e = getenv("MATINV_BATCHED");
-        mode = e ? atoi(e) : 1;  // v1 measured faster on B200 (2.1e7 vs 1.7e7 inv/s)
+        mode = e ? atoi(e) : 3;
     }
     return mode;
 }
 
 cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st) {
     if (batched_mode() >= 1) {
-        if (n == 64 && batched_mode() >= 2) return launch_batched_row64(A, batch, X, info, st);
+        if ((n == 64 || n == 32) && batched_mode() >= 3) return launch_batched_pk(A, n, batch, X, info, st);
+        if (n == 64 && batched_mode() == 2) return launch_batched_row64(A, batch, X, info, st);
         if (n == 64) return launch_batched_reg<64>(A, batch, X, info, st);
         if (n == 32) return launch_batched_reg<32>(A, batch, X, info, st);
     }

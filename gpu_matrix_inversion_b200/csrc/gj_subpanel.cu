@@ -490,6 +490,7 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
 cudaError_t debug_trace(int on, long long *out128) {
     cudaError_t e = cudaMemcpyToSymbol(g_trace_on, &on, sizeof(int));
     if (e == cudaSuccess && out128) e = cudaMemcpyFromSymbol(out128, g_trace, sizeof(long long) * 128);
+    if (e == cudaSuccess) e = debug_trace_pk(on, out128 ? out128 + 96 : nullptr);  // batched kernel: slots 96..103
     return e;
 }
 

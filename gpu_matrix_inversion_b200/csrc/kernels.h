@@ -45,6 +45,7 @@ void launch_panel_update(const float *in, long long ld_in, float *out, long long
                          cudaStream_t st);
 
 cudaError_t debug_trace(int on, long long *out128);
+cudaError_t debug_trace_pk(int on, long long *out8);
 int launch_panel_factor(float *Wv, long long ld, int n, int k0, int kb, float *CmT, long long ldc, int *piv, float *pv,
                         int *info, PanelState *ps, float *P0, float *P1, cudaStream_t st);
 
@@ -72,6 +73,7 @@ void launch_load(const float *A, int n, float *W, long long ld, int npad, cudaSt
 
 // ---- gj_batched.cu : n <= 128, one CTA per matrix
 cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st);
+cudaError_t launch_batched_pk(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st);
 
 // ---- generate.cu : synthetic workloads, residual, FFMA peak
 void launch_generate(float *A, int n, long long ld, u64 seed, int kind, int col0, int ncols, cudaStream_t st);
