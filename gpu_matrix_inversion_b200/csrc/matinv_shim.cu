@@ -283,6 +283,17 @@ int ensure_lookahead() {
     return 0;
 }
 
+// MATINV_LOOKAHEAD: 0 = off, 1 = panel k+1 factored beside GEMM_B(k), 2 (default) = 1 + the pivot-row kernel and the
+// update of column block k+1 also run on the panel stream
+int lookahead_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("MATINV_LOOKAHEAD");
+        mode = e ? atoi(e) : 2;
+    }
+    return mode;
+}
+
 void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
     const long long ld = w.npad;
     const int nt = w.npad / MATINV_NB;
@@ -296,6 +307,31 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
     for (int k = 0; k < nblk; k++) {
         const int k0 = k * MATINV_NB, b = k & 1;
         const int kb = (n - k0 < MATINV_NB) ? n - k0 : MATINV_NB;
+        if (k + 1 < nblk && lookahead_mode() == 2) {
+            // Column block k+1 goes through its own chain on the high-priority stream -- pivot rows, update, then the
+            // factorisation of panel k+1 -- while this stream does the same two steps for every other column block.
+            // The chain needs GEMM_B(k-1) (which updated block k+1) and leaves ev_p for the next iteration.
+            const int k1 = k0 + MATINV_NB;
+            const int kb1 = (n - k1 < MATINV_NB) ? n - k1 : MATINV_NB;
+            cudaEventRecord(g.ev_a, st);   // everything up to GEMM_B(k-1) (and panel k, joined below / before the loop)
+            cudaStreamWaitEvent(sp, g.ev_a, 0);
+            launch_rowblock_ex(w.W + k1, ld, MATINV_NB, k0, kb, 0, 0, CmT[b], ld, pv[b], ps[b], w.U + k1, ld, sp);
+            launch_trailing_gemm_ex(w.W + k1, ld, nt, 1, k, -1, 0, kb, CmT[b], ld, w.U + k1, ld, sp);
+            COUNT_LAUNCH(launch_panel_factor(w.W + k1, ld, n, k1, kb1, CmT[b ^ 1], ld, w.piv, pv[b ^ 1], w.info, ps[b ^ 1], w.P[0],
+                                             w.P[1], sp));
+            cudaEventRecord(g.ev_p, sp);
+            launch_rowblock_ex(w.W, ld, w.npad, k0, kb, k, 2, CmT[b], ld, pv[b], ps[b], w.U, ld, st);
+            if (g_prof.on) cudaEventRecord(prof_event(), st);
+            launch_trailing_gemm_ex(w.W, ld, nt, nt, k, k, 2, kb, CmT[b], ld, w.U, ld, st);
+            if (g_prof.on) {
+                cudaEventRecord(prof_event(), st);
+                const double m = (double)(w.npad - MATINV_NB);
+                g_prof.gemm_flops += 2.0 * m * (m - MATINV_NB) * kb;   // block k+1 is updated on the other stream
+            }
+            cudaStreamWaitEvent(st, g.ev_p, 0);
+            COUNT_LAUNCH(4);
+            continue;
+        }
         launch_rowblock(w.W, ld, w.npad, k0, kb, CmT[b], ld, pv[b], ps[b], w.U, ld, st);
         COUNT_LAUNCH(1);
         if (g_prof.on) cudaEventRecord(prof_event(), st);
@@ -326,12 +362,7 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
 }
 
 bool use_lookahead(int n, int npad) {
-    static int mode = -1;
-    if (mode < 0) {
-        const char *e = getenv("MATINV_LOOKAHEAD");
-        mode = (e && e[0] == '0') ? 0 : 1;
-    }
-    return mode == 1 && use_panel_v1(n) && npad >= 8 * MATINV_NB;
+    return lookahead_mode() >= 1 && use_panel_v1(n) && npad >= 8 * MATINV_NB;
 }
 
 // load + factorisation + column gather list; leaves M = inv(P A) in the workspace

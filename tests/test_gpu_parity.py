@@ -150,6 +150,44 @@ def test_batched_bit_exact(m, n):
             assert np.array_equal(bits(X[b]), bits(Xo)), b
 
 
+@pytest.mark.parametrize("n", [32, 64])
+def test_batched_edge_cases(m, n):
+    """The register-resident batched kernels against the oracle on inputs that stress the bookkeeping rather than the
+    arithmetic: ties in magnitude (lowest row wins), exact zeros and signed zeros (the pivot column is seeded with +0),
+    permutation matrices (every step swaps), denormals, and non-finite entries (flagged, never compared)."""
+    rng = np.random.default_rng(1234 + n)
+    mats = []
+    for _ in range(12):                                     # small integers: ties and exact zeros everywhere
+        mats.append(rng.integers(-2, 3, size=(n, n)).astype(np.float32))
+    for _ in range(4):                                      # permutation matrices, some with negative entries
+        P = np.eye(n, dtype=np.float32)[rng.permutation(n)]
+        mats.append(P * rng.choice([-1.0, 1.0], size=(n, 1)).astype(np.float32))
+    mats.append(np.eye(n, dtype=np.float32)[::-1].copy())   # anti-diagonal
+    H = o.batched(n, 100, 4)
+    H[0][rng.random((n, n)) < 0.7] = 0.0                     # sparse, most likely singular
+    H[1][np.arange(n), np.arange(n)] = 0.0                   # hollow: zero diagonal
+    H[2] *= np.float32(1e-41)                                # denormal entries
+    H[3][:, 3] = -H[3][:, 3]
+    H[3][5, :] = -0.0
+    H[3][5, 5] = 1.0
+    mats.extend(H)
+    bad = o.batched(n, 200, 3)
+    bad[0][n // 2, n // 3] = np.nan
+    bad[1][1, 1] = np.inf
+    bad[2][0, 0] = np.nan                                    # NaN in the very first pivot candidate
+    mats.extend(bad)
+    A = np.ascontiguousarray(np.stack(mats), dtype=np.float32)
+    X, info = m.invert_batched(A)
+    nonsingular = 0
+    for b in range(A.shape[0]):
+        Xo, _, io = o.invert_inplace(A[b])
+        assert (info[b] != 0) == (io != 0), (b, info[b], io)
+        if io == 0:
+            nonsingular += 1
+            assert np.array_equal(bits(X[b]), bits(Xo)), b
+    assert nonsingular >= 6
+
+
 def test_batched_full_size_properties(m):
     """configs[3] at reduced batch: 64x64, 16384 matrices; checksum-of-residuals property + spot bit-exactness."""
     import torch
