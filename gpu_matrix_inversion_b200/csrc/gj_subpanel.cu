@@ -275,16 +275,17 @@ subpanel_kernel(const float *__restrict__ in, long long ld_in, float *__restrict
 }
 
 // ------------------------------------------------------------------------------------------ update of the rest of the panel
+template <int ROWS>
 struct __align__(16) UpdSmem {
     float old_[32][MATINV_NB];   // original contents of every row touched by the sub-panel's swaps
     float us[16][MATINV_NB];     // U snapshot of the sub-panel steps
     float xf[16][MATINV_NB];     // final contents of the sub-panel's pivot rows
-    float cs[16][MATINV_RB];     // multipliers of my 64 rows
+    float cs[16][ROWS];          // multipliers of my rows
     float cp[16][16];            // multipliers of the pivot rows
     float pv[16];
     int pos[32], content[32];
     int m;
-    int rowmap[MATINV_RB];       // my row -> slot in pos[] or -1
+    int rowmap[ROWS];            // my row -> slot in pos[] or -1
 };
 
 // Net permutation of the sub-panel's sw (<= 16) row interchanges, one warp, no serial search: every lane tracks ONE
@@ -325,12 +326,20 @@ __device__ __forceinline__ void build_subperm(const int *__restrict__ piv, int r
     if (lane == 0) *mout = 32;
 }
 
-__global__ void __launch_bounds__(256)
+// ROWS rows per CTA.  Everything before the main loop (permutation, gather of the touched rows, 16-step recurrence on
+// the pivot rows) is the same for every CTA and is a latency chain of ~12k cycles, the update itself is ~1.5k cycles
+// per 64 rows: with 256 rows per CTA the kernel holds a quarter of the SM slots for about the same time, which is what
+// matters when it runs beside the trailing update (look-ahead): its CTAs displace GEMM CTAs for as long as they live.
+template <int ROWS>
+__global__ void __launch_bounds__(256, 2)   // <= 128 registers: a CTA must fit beside one CTA of the trailing update
 panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__restrict__ out, long long ld_out, int n,
                     int k0, int s0, int sw, int wfull, float *__restrict__ CmT, long long ldc,
                     const int *__restrict__ piv, const float *__restrict__ pvg, PanelState *__restrict__ ps, int kb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    UpdSmem &s = *reinterpret_cast<UpdSmem *>(smem_raw);
+    UpdSmem<ROWS> &s = *reinterpret_cast<UpdSmem<ROWS> *>(smem_raw);
+    constexpr int RPW = ROWS / 8;   // rows per warp
+    constexpr int GR = 4;           // rows per group (their 16-step chains are interleaved)
+    constexpr int NG = RPW / GR;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = k0 + s0;
     const int trace_on = g_trace_on;
@@ -398,32 +407,32 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
         return;
     }
 
-    // ===== regular CTA: rows [i0, i0 + 64)
-    const int i0 = blockIdx.x * MATINV_RB;
-    // my 8 rows are fetched up front: the loads fly while the permutation / recurrence prologue runs
-    float4 pre[8];
+    // ===== regular CTA: rows [i0, i0 + ROWS), warp w owns rows i0 + w*RPW + [0, RPW) in groups of GR
+    const int i0 = blockIdx.x * ROWS;
+    // the first group of rows is fetched up front: the loads fly while the permutation / recurrence prologue runs
+    float4 pre[GR];
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const int i = i0 + warp * 8 + q;
+    for (int q = 0; q < GR; q++) {
+        const int i = i0 + warp * RPW + q;
         pre[q] = (i < n) ? *reinterpret_cast<const float4 *>(in + (long long)i * ld_in + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (warp == 0) build_subperm(piv, r0, sw, s.pos, s.content, &s.m);
-    for (int e = tid; e < 16 * MATINV_RB; e += 256) {
-        const int t = e / MATINV_RB, ii = e - t * MATINV_RB;
+    for (int e = tid; e < 16 * ROWS; e += 256) {
+        const int t = e / ROWS, ii = e - t * ROWS;
         s.cs[t][ii] = (t < sw && i0 + ii < n) ? CmT[(long long)(s0 + t) * ldc + i0 + ii] : 0.0f;
     }
+    for (int ii = tid; ii < ROWS; ii += 256) s.rowmap[ii] = -1;
     {
         const int t = tid >> 4, t2 = tid & 15;
         s.cp[t][t2] = (t < sw && t2 < sw) ? CmT[(long long)(s0 + t) * ldc + r0 + t2] : 0.0f;
         if (tid < 16) s.pv[tid] = (tid < sw) ? pvg[s0 + tid] : 1.0f;
-        if (tid < MATINV_RB) s.rowmap[tid] = -1;
     }
     __syncthreads();
     TRACE(blockIdx.x == 3, 33);
     const int m = s.m;
     if (tid < m && s.pos[tid] >= 0) {
         const int ii = s.pos[tid] - i0;
-        if (ii >= 0 && ii < MATINV_RB) s.rowmap[ii] = tid;
+        if (ii >= 0 && ii < ROWS) s.rowmap[ii] = tid;
     }
     for (int e = tid; e < m * 32; e += 256) {
         const int idx = e >> 5, f = e & 31;
@@ -462,27 +471,44 @@ panel_update_kernel(const float *__restrict__ in, long long ld_in, float *__rest
     float4 us[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) us[t] = *reinterpret_cast<const float4 *>(&s.us[t][4 * lane]);
+#pragma unroll 2
+    for (int g = 0; g < NG; g++) {
+        const int ii0 = warp * RPW + g * GR;
+        // GR rows at a time, the 16-step chains interleaved: rows touched by a swap start from their permuted contents,
+        // the sub-panel's own pivot rows take the recurrence result afterwards (their chain is discarded)
+        float4 acc[GR];
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const int ii = warp * 8 + q, i = i0 + ii;
-        if (i >= n) continue;  // warp-uniform
-        float4 acc;
-        if (i >= r0 && i < r0 + sw) {
-            acc = *reinterpret_cast<const float4 *>(&s.xf[i - r0][4 * lane]);
-        } else {
-            const int slot = s.rowmap[ii];
-            if (slot >= 0) acc = *reinterpret_cast<const float4 *>(&s.old_[s.content[slot]][4 * lane]);
-            else acc = pre[q];
+        for (int q = 0; q < GR; q++) {
+            const int slot = s.rowmap[ii0 + q];
+            acc[q] = pre[q];
+            if (slot >= 0) acc[q] = *reinterpret_cast<const float4 *>(&s.old_[s.content[slot]][4 * lane]);
+        }
+        if (g + 1 < NG) {   // next group's rows fly during this group's FMAs
 #pragma unroll
-            for (int t = 0; t < 16; t++) {
-                const float c = s.cs[t][ii];  // zero beyond sw: fma(-0, 0, a) == a
-                acc.x = gj_elim(acc.x, c, us[t].x);
-                acc.y = gj_elim(acc.y, c, us[t].y);
-                acc.z = gj_elim(acc.z, c, us[t].z);
-                acc.w = gj_elim(acc.w, c, us[t].w);
+            for (int q = 0; q < GR; q++) {
+                const int i = i0 + ii0 + GR + q;
+                pre[q] = (i < n) ? *reinterpret_cast<const float4 *>(in + (long long)i * ld_in + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        if (!own_cols) *reinterpret_cast<float4 *>(out + (long long)i * ld_out + 4 * lane) = acc;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            const float4 ca = *reinterpret_cast<const float4 *>(&s.cs[t][ii0]);      // zero beyond sw: fma(-0, 0, a) == a
+            const float c[GR] = {ca.x, ca.y, ca.z, ca.w};
+#pragma unroll
+            for (int q = 0; q < GR; q++) {
+                acc[q].x = gj_elim(acc[q].x, c[q], us[t].x);
+                acc[q].y = gj_elim(acc[q].y, c[q], us[t].y);
+                acc[q].z = gj_elim(acc[q].z, c[q], us[t].z);
+                acc[q].w = gj_elim(acc[q].w, c[q], us[t].w);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < GR; q++) {
+            const int i = i0 + ii0 + q;
+            if (i >= n) continue;  // warp-uniform
+            if (i >= r0 && i < r0 + sw) acc[q] = *reinterpret_cast<const float4 *>(&s.xf[i - r0][4 * lane]);
+            if (!own_cols) *reinterpret_cast<float4 *>(out + (long long)i * ld_out + 4 * lane) = acc[q];
+        }
     }
     TRACE(blockIdx.x == 3, 36);
 }
@@ -539,16 +565,35 @@ cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long l
 #undef SP_ARGS
 }
 
+template <int ROWS>
+static void launch_panel_update_t(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0, int sw,
+                                  int wfull, float *CmT, long long ldc, const int *piv, const float *pv, PanelState *ps, int kb,
+                                  cudaStream_t st) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
+        cudaFuncSetAttribute(panel_update_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem<ROWS>));
+    }
+    const int nblk = (n + ROWS - 1) / ROWS + 1;
+    panel_update_kernel<ROWS><<<nblk, 256, sizeof(UpdSmem<ROWS>), st>>>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv,
+                                                                        pv, ps, kb);
+}
+
+// Rows per CTA: 64 while that is a single wave of CTAs (the kernel is then on the critical path of a panel-bound
+// inversion: 12.3 ms against 14.2 ms at n = 4096), 256 above (it runs beside the trailing update and the time its CTAs
+// hold SM slots is what counts: 171.7 ms against 178.5 ms at n = 16384).  MATINV_UPDATE_ROWS = 64 | 128 | 256 | 512 overrides.
 void launch_panel_update(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0, int sw,
                          int wfull, float *CmT, long long ldc, const int *piv, const float *pv, PanelState *ps, int kb,
                          cudaStream_t st) {
-    static bool configured[64] = {};
-    if (first_use_on_device(configured)) {
-        cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem));
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("MATINV_UPDATE_ROWS");
+        forced = e ? atoi(e) : 0;
     }
-    const int nblk = (n + MATINV_RB - 1) / MATINV_RB + 1;
-    panel_update_kernel<<<nblk, 256, sizeof(UpdSmem), st>>>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv,
-                                                            pv, ps, kb);
+    const int rows = forced ? forced : (n <= 64 * 148 ? 64 : 256);
+    if (rows == 64) launch_panel_update_t<64>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
+    else if (rows == 128) launch_panel_update_t<128>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
+    else if (rows == 512) launch_panel_update_t<512>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
+    else launch_panel_update_t<256>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
 }
 
 // Whole panel (kb <= 128 columns starting at global row/column k0) of a column view `Wv` (leading dimension ld): 8
