@@ -284,7 +284,8 @@ int ensure_lookahead() {
 }
 
 // MATINV_LOOKAHEAD: 0 = off, 1 = panel k+1 factored beside GEMM_B(k), 2 (default) = 1 + the pivot-row kernel and the
-// update of column block k+1 also run on the panel stream
+// update of column block k+1 also run on the panel stream.  (Splitting the remaining columns into two ranges on two
+// streams, so that one range's pivot-row kernel overlaps the other's update, was measured slower: 174.7 vs 172.2 ms.)
 int lookahead_mode() {
     static int mode = -1;
     if (mode < 0) {
@@ -307,7 +308,7 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
     for (int k = 0; k < nblk; k++) {
         const int k0 = k * MATINV_NB, b = k & 1;
         const int kb = (n - k0 < MATINV_NB) ? n - k0 : MATINV_NB;
-        if (k + 1 < nblk && lookahead_mode() == 2) {
+        if (k + 1 < nblk && lookahead_mode() >= 2) {
             // Column block k+1 goes through its own chain on the high-priority stream -- pivot rows, update, then the
             // factorisation of panel k+1 -- while this stream does the same two steps for every other column block.
             // The chain needs GEMM_B(k-1) (which updated block k+1) and leaves ev_p for the next iteration.
