@@ -559,7 +559,20 @@ cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long l
         while (ncta * 512 < n) ncta *= 2;
         return launch_subpanel_t<16, 1, 512>(ncta, SP_ARGS);
     }
-    if (n <= 16384) return launch_subpanel_t<16, 2, 512>(16, SP_ARGS);
+    if (n <= 16384) {
+        // Two shapes for the same 16 x n sub-panel.  512 threads x 2 rows is the faster kernel (25 vs 31 us) and is used
+        // while the panel is on the critical path; from n = 12288 the panel is hidden behind the trailing update and what
+        // counts is what its CTAs displace: 256 threads x 4 rows stay within 128 registers, so a CTA fits beside one CTA of
+        // the trailing update instead of taking the whole SM (N=16384: 171.8 -> 169.0 ms).  MATINV_K1_THREADS overrides.
+        static int forced = -1;
+        if (forced < 0) {
+            const char *e = getenv("MATINV_K1_THREADS");
+            forced = e ? atoi(e) : 0;
+        }
+        const int th = forced ? forced : (n >= 12288 ? 256 : 512);
+        if (th == 256) return launch_subpanel_t<16, 4, 256>(16, SP_ARGS);
+        return launch_subpanel_t<16, 2, 512>(16, SP_ARGS);
+    }
     if (n <= 32768) return launch_subpanel_t<16, 4, 512>(16, SP_ARGS);
     return launch_subpanel_t<8, 8, 512>(16, SP_ARGS);
 #undef SP_ARGS
