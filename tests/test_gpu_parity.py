@@ -276,3 +276,56 @@ def test_device_entry_on_a_side_stream(m):
     s.synchronize()
     assert rc == m.OK
     assert np.array_equal(bits(X.cpu().numpy()), bits(o.invert_inplace(o.diagdom(n))[0]))
+
+
+_SWITCH_PROBE = r"""
+import hashlib, sys
+import torch
+import gpu_matrix_inversion_b200 as m
+from oracle.gj_oracle import SEED_BATCHED, SEED_UNIFORM
+out = []
+for n in (1500, 8320):
+    A = m.generate_dev(n, SEED_UNIFORM + n, "uniform")
+    piv = torch.empty(n, dtype=torch.int32, device="cuda")
+    rc, X = m.invert_dev(A, piv=piv)
+    assert rc == 0
+    out.append(hashlib.sha256(X.cpu().numpy().tobytes() + piv.cpu().numpy().tobytes()).hexdigest())
+B = m.generate_batched_dev(64, 0, 512, SEED_BATCHED)
+Xb, info = m.invert_batched_dev(B)
+out.append(hashlib.sha256(Xb.cpu().numpy().tobytes() + info.cpu().numpy().tobytes()).hexdigest())
+print("HASHES", *out)
+"""
+
+
+def test_tuning_switches_bit_identical(m):
+    """Every MATINV_* switch selects between schedules / kernel shapes of the same arithmetic: the inverse, the pivot
+    sequence and the batched results must not change by a single bit.  The switches are read once per process, so each
+    setting runs in a fresh interpreter; N=1500 goes through the look-ahead schedule with the small-N kernel shapes,
+    N=8320 through the large-N ones (256-row update CTAs, 64-column pivot-row CTAs, both sub-panel shapes)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    settings = [{}, {"MATINV_LOOKAHEAD": "0"}, {"MATINV_LOOKAHEAD": "1"}, {"MATINV_PANEL": "0"},
+                {"MATINV_UPDATE_ROWS": "256", "MATINV_ROWBLOCK_CW": "128", "MATINV_K1_THREADS": "256"},
+                {"MATINV_UPDATE_ROWS": "64", "MATINV_ROWBLOCK_CW": "32", "MATINV_K1_THREADS": "512", "MATINV_GEMM": "0"},
+                {"MATINV_BATCHED": "1", "MATINV_GEMM": "3"}, {"MATINV_BATCHED": "0", "MATINV_UPDATE_ROWS": "128"}]
+    seen = []
+    for extra in settings:
+        env = {k: v for k, v in os.environ.items() if not k.startswith("MATINV_")}
+        env.update(extra)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        r = subprocess.run([sys.executable, "-c", _SWITCH_PROBE], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (extra, r.stderr[-2000:])
+        line = [l for l in r.stdout.splitlines() if l.startswith("HASHES")][-1]
+        seen.append((extra, line.split()[1:]))
+    ref = seen[0][1]
+    for extra, hashes in seen[1:]:
+        assert hashes == ref, (extra, hashes, ref)
+    # and the default is the oracle's answer (N=1500 is small enough for the CPU replay)
+    import hashlib
+
+    Xo, po, io = o.invert_inplace(o.generate(1500, o.SEED_UNIFORM + 1500, "uniform"))
+    assert io == 0
+    assert hashlib.sha256(Xo.tobytes() + np.asarray(po, dtype=np.int32).tobytes()).hexdigest() == ref[0]
