@@ -6,7 +6,7 @@ OUT       := gpu_matrix_inversion_b200/libmatinv32.so
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O3 \
              --expt-relaxed-constexpr -Xptxas -v
 CU        := $(wildcard $(CSRC)/*.cu)
-OBJ       := $(CU:.cu=.o) $(CSRC)/mat_inv_32.o
+OBJ       := $(CU:.cu=.o) $(CSRC)/mat_inv_32.o $(CSRC)/matrix_inversion.o
 
 all: $(OUT) oracle
 
@@ -14,6 +14,9 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h include/matinv_sh
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
 
 $(CSRC)/mat_inv_32.o: $(CSRC)/mat_inv_32.cpp include/mat_inv_32.h include/matinv_shim.h
+	g++ -O2 -std=c++17 -fPIC -c $< -o $@
+
+$(CSRC)/matrix_inversion.o: $(CSRC)/matrix_inversion.cpp include/matrix_inversion.h include/mat_inv_32.h include/matinv_shim.h
 	g++ -O2 -std=c++17 -fPIC -c $< -o $@
 
 $(OUT): $(OBJ)

@@ -25,7 +25,7 @@ __all__ = ["lib", "matrix_inv_32", "invert", "invert_dev", "invert_batched", "in
 
 OK, SINGULAR = 0, 1
 E_INVALID, E_NODEVICE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
-FLAG_TF32X3, FLAG_UNBLOCKED, FLAG_VERBOSE, FLAG_NOCHECK = 1, 2, 4, 8
+FLAG_TF32X3, FLAG_UNBLOCKED, FLAG_VERBOSE, FLAG_NOCHECK, FLAG_NOPIVOT = 1, 2, 4, 8, 16
 
 _SO = Path(__file__).resolve().parent / "libmatinv32.so"
 
@@ -37,7 +37,8 @@ EXPORTS = [
     "matinv_shard_generate", "matinv_shard_factor",
     "matinv_shard_apply", "matinv_shard_apply_ex", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
-    "matinv_profile_read", "matinv_debug_trace",
+    "matinv_profile_read", "matinv_debug_trace", "matinv_invert_f64", "matinv_invert_f64_dev", "matinv_residual_f64_dev",
+    "matinv_host_defect_f64",
 ]
 
 
@@ -65,6 +66,10 @@ def _load() -> ctypes.CDLL:
     L.matinv_generate_f32_dev.argtypes = [fp, i, ll, ull, i, i, i, vp]
     L.matinv_generate_batched_f32_dev.argtypes = [fp, i, ll, ll, ull, vp]
     L.matinv_residual_f32_dev.argtypes = [fp, fp, i, dp, vp]
+    L.matinv_invert_f64.argtypes = [fp, i, fp, ip, i]
+    L.matinv_invert_f64_dev.argtypes = [fp, i, fp, ip, vp, i]
+    L.matinv_residual_f64_dev.argtypes = [fp, fp, i, dp, vp]
+    L.matinv_host_defect_f64.argtypes = [fp, fp, i, dp]
     L.matinv_last_timing.argtypes = [dp, dp]
     L.matinv_ffma_peak_tflops.argtypes = [dp, vp]
     L.matinv_profile_enable.argtypes = [i]
@@ -93,7 +98,8 @@ def _load() -> ctypes.CDLL:
     for name in ("matinv_invert_f32", "matinv_invert_f32_dev", "matinv_invert_batched_f32",
                  "matinv_invert_batched_f32_dev", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
                  "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_shard_create",
-                 "matinv_shard_generate", "matinv_shard_factor", "matinv_shard_apply", "matinv_shard_status"):
+                 "matinv_shard_generate", "matinv_shard_factor", "matinv_shard_apply", "matinv_shard_status",
+                 "matinv_invert_f64", "matinv_invert_f64_dev", "matinv_residual_f64_dev", "matinv_host_defect_f64"):
         getattr(L, name).restype = i
     return L
 
@@ -151,6 +157,73 @@ def matrix_inv_32(matrix_vector, matrix_order: int) -> np.ndarray:
     except MatinvError:
         return np.empty(0, dtype=np.float32)
     return np.empty(0, dtype=np.float32) if X is None else X.ravel()
+
+
+def invert_f64(A: np.ndarray, nopivot: bool = False, want_piv: bool = False, flags: int = 0):
+    """FP64 inversion from host memory (device side of matrix_inversion_FP64 / matrix_inversion_no_pivots).  Returns X
+    (None when singular) and, if want_piv, the pivot vector (the identity permutation with nopivot)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    if A.ndim != 2 or A.shape[1] != n:
+        raise ValueError("square matrix expected")
+    X = np.empty_like(A)
+    piv = np.empty(n, dtype=np.int32) if want_piv else None
+    f = flags | (FLAG_NOPIVOT if nopivot else 0)
+    rc = _check(lib.matinv_invert_f64(A.ctypes.data, n, X.ctypes.data, piv.ctypes.data if want_piv else None, f))
+    X = X if rc == OK else None
+    return (X, piv) if want_piv else X
+
+
+def _vector_f64(matrix_vector, matrix_order: int, nopivot: bool) -> np.ndarray:
+    v = np.ascontiguousarray(matrix_vector, dtype=np.float64).ravel()
+    n = int(matrix_order)
+    if n <= 0 or v.size // n != n:
+        return np.empty(0, dtype=np.float64)
+    try:
+        X = invert_f64(v[: n * n].reshape(n, n), nopivot=nopivot)
+    except MatinvError:
+        return np.empty(0, dtype=np.float64)
+    return np.empty(0, dtype=np.float64) if X is None else X.ravel()
+
+
+def matrix_inversion_FP64(matrix_vector, matrix_order: int) -> np.ndarray:
+    """Python twin of `std::vector<double> matrix_inversion_FP64(std::vector<double>, int)`
+    (matrix_inversion_FP64.cpp:13, checks :209-217): empty result for invalid or singular input."""
+    return _vector_f64(matrix_vector, matrix_order, False)
+
+
+def matrix_inversion_no_pivots(matrix_vector, matrix_order: int) -> np.ndarray:
+    """Python twin of `matrix_inversion_no_pivots` (matrix_inversion_no_pivots.cpp:10): no row interchanges."""
+    return _vector_f64(matrix_vector, matrix_order, True)
+
+
+def matrix_multiply(matriceB, matriceA) -> float:
+    """Python twin of `double matrix_multiply(std::vector<double> B, std::vector<double> A)` (matrix_multiply.cpp:15-212):
+    sqrt(order) - ||A B||_F, computed on the device."""
+    A = np.ascontiguousarray(matriceA, dtype=np.float64).ravel()
+    B = np.ascontiguousarray(matriceB, dtype=np.float64).ravel()
+    n = int(round(np.sqrt(A.size)))
+    if n <= 0 or n * n != A.size or B.size != A.size:
+        return float("nan")
+    out = (ctypes.c_double * 4)()
+    _check(lib.matinv_host_defect_f64(A.ctypes.data, B.ctypes.data, n, out))
+    return float(np.sqrt(n) - np.sqrt(out[3]))
+
+
+def invert_f64_dev(A, X=None, piv=None, nopivot: bool = False, flags: int = 0):
+    """Device-resident FP64 inversion on torch's current stream; A: (n,n) float64 CUDA tensor."""
+    import torch
+
+    assert A.is_cuda and A.dtype == torch.float64 and A.is_contiguous() and A.dim() == 2 and A.shape[0] == A.shape[1]
+    if X is None:
+        X = torch.empty_like(A)
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    f = flags | (FLAG_NOPIVOT if nopivot else 0)
+    with torch.cuda.device(A.device):
+        rc = lib.matinv_invert_f64_dev(_torch_ptr(A), A.shape[0], _torch_ptr(X),
+                                       _torch_ptr(piv) if piv is not None else None, ctypes.c_void_p(st), f)
+    _check(rc)
+    return rc, X
 
 
 def _torch_ptr(t):

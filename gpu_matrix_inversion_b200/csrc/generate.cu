@@ -41,11 +41,12 @@ __global__ void __launch_bounds__(256) generate_batched_kernel(float *__restrict
 }
 
 // 64x64 tile of R = A X, FP64 accumulate, 256 threads x (4x4).
-__global__ void __launch_bounds__(256) residual_kernel(const float *__restrict__ A, const float *__restrict__ X, int n,
+template <typename T>
+__global__ void __launch_bounds__(256) residual_kernel(const T *__restrict__ A, const T *__restrict__ X, int n,
                                                        double *__restrict__ out) {
-    __shared__ float sa[16][64 + 1];
-    __shared__ float sx[16][64];
-    __shared__ double red[3][8];
+    __shared__ T sa[16][64 + 1];
+    __shared__ T sx[16][64];
+    __shared__ double red[4][8];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
     double acc[4][4] = {};
@@ -53,13 +54,13 @@ __global__ void __launch_bounds__(256) residual_kernel(const float *__restrict__
     for (int k0 = 0; k0 < n; k0 += 16) {
         for (int e = threadIdx.x; e < 64 * 16; e += 256) {
             const int ii = e >> 4, kk = e & 15;
-            const float v = (i0 + ii < n && k0 + kk < n) ? A[(long long)(i0 + ii) * n + k0 + kk] : 0.0f;
+            const T v = (i0 + ii < n && k0 + kk < n) ? A[(long long)(i0 + ii) * n + k0 + kk] : (T)0;
             sa[kk][ii] = v;
             if (blockIdx.x == 0) a2 += (double)v * (double)v;
         }
         for (int e = threadIdx.x; e < 16 * 64; e += 256) {
             const int kk = e >> 6, jj = e & 63;
-            const float v = (k0 + kk < n && j0 + jj < n) ? X[(long long)(k0 + kk) * n + j0 + jj] : 0.0f;
+            const T v = (k0 + kk < n && j0 + jj < n) ? X[(long long)(k0 + kk) * n + j0 + jj] : (T)0;
             sx[kk][jj] = v;
             if (blockIdx.y == 0) x2 += (double)v * (double)v;
         }
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) residual_kernel(const float *__restrict__
         }
         __syncthreads();
     }
-    double r2 = 0.0;
+    double r2 = 0.0, p2 = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; q++)
 #pragma unroll
@@ -85,17 +86,18 @@ __global__ void __launch_bounds__(256) residual_kernel(const float *__restrict__
             if (i < n && j < n) {
                 const double d = acc[q][w] - (i == j ? 1.0 : 0.0);
                 r2 += d * d;
+                p2 += acc[q][w] * acc[q][w];
             }
         }
-    double vals[3] = {r2, a2, x2};
+    double vals[4] = {r2, a2, x2, p2};   // out[3] = ||A X||_F^2 (the reference's "Frobenius defect" is sqrt(n) - its root)
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
+    for (int q = 0; q < 4; q++) {
         double v = vals[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 4) {
         double v = 0.0;
         for (int w = 0; w < 8; w++) v += red[threadIdx.x][w];
         atomicAdd(out + threadIdx.x, v);
@@ -151,17 +153,26 @@ void launch_generate_batched(float *A, int n, long long first, long long count, 
     generate_batched_kernel<<<148 * 16, 256, 0, st>>>(A, n, first, count, seed0);
 }
 
-cudaError_t run_residual(const float *A, const float *X, int n, double *out_host, cudaStream_t st) {
+template <typename T>
+static cudaError_t run_residual_t(const T *A, const T *X, int n, double *out_host, int nout, cudaStream_t st) {
     double *d = nullptr;
-    cudaError_t e = cudaMalloc(&d, 3 * sizeof(double));
+    cudaError_t e = cudaMalloc(&d, 4 * sizeof(double));
     if (e != cudaSuccess) return e;
-    cudaMemsetAsync(d, 0, 3 * sizeof(double), st);
+    cudaMemsetAsync(d, 0, 4 * sizeof(double), st);
     dim3 grid((n + 63) / 64, (n + 63) / 64);
-    residual_kernel<<<grid, 256, 0, st>>>(A, X, n, d);
-    e = cudaMemcpyAsync(out_host, d, 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    residual_kernel<T><<<grid, 256, 0, st>>>(A, X, n, d);
+    e = cudaMemcpyAsync(out_host, d, nout * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);
     return e;
+}
+
+cudaError_t run_residual(const float *A, const float *X, int n, double *out_host, cudaStream_t st) {
+    return run_residual_t<float>(A, X, n, out_host, 3, st);
+}
+
+cudaError_t run_residual_f64(const double *A, const double *X, int n, double *out_host, cudaStream_t st) {
+    return run_residual_t<double>(A, X, n, out_host, 4, st);
 }
 
 cudaError_t run_ffma_peak(double *tflops, cudaStream_t st) {

@@ -1,0 +1,243 @@
+// FP64 Gauss-Jordan inversion, with and without partial pivoting: the device side of
+//   std::vector<double> matrix_inversion_FP64(std::vector<double>, int)
+//       /root/reference/matrix_inv_solution/matrix_inversion_solution/matrix_inversion/matrix_inversion_FP64.cpp:13
+//   std::vector<double> matrix_inversion_no_pivots(std::vector<double>, int)
+//       .../matrix_inversion_no_pivots.cpp:10  (findCrr :41, fixRowKernel :60, copyCirColumn :50, fixColumnKernel :15)
+// (the entry points next to the FP32 hot path.)
+//
+// Round-1 form: the UNBLOCKED in-place schedule of gj_unblocked.cu in double precision -- three launches per column
+// (arg max, swap + normalise, rank-1 update), bit-identical to oracle/gj_oracle.c:gj_inplace_f64.  The rank-1 update
+// reads and writes the whole matrix once per column, so this path is HBM-bound (16 N^3 bytes): the roofline reported
+// for it is the copy bandwidth, not the FP64 pipe.  A blocked FP64 trailing update is the obvious next step.
+//
+// The pivot candidate cannot ride in one 64-bit key as in FP32 (|x| alone is 63 bits), so partial results are
+// (magnitude bits, row, value) triples compared lexicographically: larger magnitude, then lower row.  The NaN rules are
+// those of common.cuh:gj_mag -- a NaN candidate never wins, a NaN incumbent (row r itself) is never displaced.
+#include "common.cuh"
+#include "kernels.h"
+
+struct __align__(8) PivCand {
+    u64 mag;      // bits of |x| (0 for a NaN that is not the incumbent, all ones for a NaN incumbent)
+    double val;   // the signed entry
+    int row;      // 0x7FFFFFFF = no candidate
+    int pad;
+};
+
+__device__ __forceinline__ u64 gj_mag64(double x, bool incumbent) {
+    const double a = fabs(x);
+    return (a == a) ? (u64)__double_as_longlong(a) : (incumbent ? ~0ull : 0ull);
+}
+__device__ __forceinline__ bool cand_better(u64 m1, int r1, u64 m2, int r2) { return m1 > m2 || (m1 == m2 && r1 < r2); }
+
+__device__ __forceinline__ void warp_best(u64 &mag, int &row, double &val) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 m2 = __shfl_xor_sync(0xffffffffu, mag, o);
+        const int r2 = __shfl_xor_sync(0xffffffffu, row, o);
+        const double v2 = __shfl_xor_sync(0xffffffffu, val, o);
+        if (cand_better(m2, r2, mag, row)) { mag = m2; row = r2; val = v2; }
+    }
+}
+
+// CTA-wide best of (mag,row,val); valid in every thread of warp 0 afterwards (sm: 8 entries each)
+__device__ __forceinline__ void block_best(u64 &mag, int &row, double &val, u64 *smag, int *srow, double *sval) {
+    warp_best(mag, row, val);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { smag[warp] = mag; srow[warp] = row; sval[warp] = val; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        mag = (lane < nw) ? smag[lane] : 0ull;
+        row = (lane < nw) ? srow[lane] : 0x7FFFFFFF;
+        val = (lane < nw) ? sval[lane] : 0.0;
+        warp_best(mag, row, val);
+    }
+}
+
+// (1) one partial per 256 rows of column `col`, rows >= row0
+__global__ void __launch_bounds__(256) argmax_f64_kernel(const double *__restrict__ W, long long ld, int n, int col, int row0,
+                                                         PivCand *__restrict__ part) {
+    __shared__ u64 smag[8];
+    __shared__ int srow[8];
+    __shared__ double sval[8];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    u64 mag = 0;
+    int row = 0x7FFFFFFF;
+    double val = 0.0;
+    if (i >= row0 && i < n) {
+        val = W[(long long)i * ld + col];
+        mag = gj_mag64(val, i == row0);
+        row = i;
+    }
+    block_best(mag, row, val, smag, srow, sval);
+    if (threadIdx.x == 0) {
+        PivCand c;
+        c.mag = mag; c.val = val; c.row = row; c.pad = 0;
+        part[blockIdx.x] = c;
+    }
+}
+
+// (1') no pivoting: the candidate is the diagonal entry itself (findCrr, matrix_inversion_no_pivots.cpp:41)
+__global__ void diag_f64_kernel(const double *__restrict__ W, long long ld, int r, PivCand *__restrict__ part) {
+    PivCand c;
+    c.val = W[(long long)r * ld + r];
+    c.mag = gj_mag64(c.val, true);
+    c.row = r;
+    c.pad = 0;
+    part[0] = c;
+}
+
+// (2) fused row swap + true division of the pivot row; thread x handles column x of the two rows and row x of the
+// multiplier column.  Every CTA reduces the partials redundantly (no grid sync).
+__global__ void __launch_bounds__(256) swap_normalize_f64_kernel(double *__restrict__ W, long long ld, int n, int r,
+                                                                 const PivCand *__restrict__ part, int nparts,
+                                                                 double *__restrict__ urow, double *__restrict__ ccol,
+                                                                 int *__restrict__ piv, int *__restrict__ info) {
+    __shared__ u64 smag[8];
+    __shared__ int srow[8];
+    __shared__ double sval[8];
+    __shared__ int sp;
+    __shared__ double sv;
+    u64 mag = 0;
+    int row = 0x7FFFFFFF;
+    double val = 0.0;
+    for (int g = threadIdx.x; g < nparts; g += 256) {
+        const PivCand c = part[g];
+        if (cand_better(c.mag, c.row, mag, row)) { mag = c.mag; row = c.row; val = c.val; }
+    }
+    block_best(mag, row, val, smag, srow, sval);
+    if (threadIdx.x == 0) { sp = row; sv = val; }
+    __syncthreads();
+    const int p = sp;
+    const double v = sv;   // carried with the candidate: W[p][r] itself is rewritten below
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x == 0) {
+        piv[r] = p;
+        if ((v == 0.0 || !isfinite(v)) && *info == 0) *info = r + 1;
+    }
+    if (x >= n) return;
+    if (x != r && x != p) ccol[x] = W[(long long)x * ld + r];
+    const double rr = W[(long long)r * ld + x];
+    const double pp = W[(long long)p * ld + x];
+    const double u = (x == r) ? 1.0 / v : pp / v;
+    urow[x] = u;
+    W[(long long)r * ld + x] = u;
+    if (p != r) W[(long long)p * ld + x] = rr;
+    if (x == r) {
+        ccol[r] = 0.0;
+        if (p != r) ccol[p] = rr;
+    }
+}
+
+// (3) W[i][j] <- fma(-c_i, u_j, W[i][j]), column r <- fma(-c_i, u_r, +0); grid (ceil(n/64), ceil(n/8)), block (32, 8),
+// two consecutive columns per thread (ld is even, so the 16-byte accesses are aligned).
+__global__ void __launch_bounds__(256) rank1_update_f64_kernel(double *__restrict__ W, long long ld, int n, int r,
+                                                               const double *__restrict__ urow,
+                                                               const double *__restrict__ ccol) {
+    const int i = blockIdx.y * 8 + threadIdx.y;
+    const int j0 = (blockIdx.x * 32 + threadIdx.x) * 2;
+    if (i >= n || j0 >= n || i == r) return;
+    const double c = ccol[i];
+    double *row = W + (long long)i * ld;
+    if (j0 + 1 < n) {
+        double2 a = *reinterpret_cast<double2 *>(row + j0);
+        const double2 u = *reinterpret_cast<const double2 *>(urow + j0);
+        a.x = (j0 == r) ? fma(-c, u.x, 0.0) : fma(-c, u.x, a.x);
+        a.y = (j0 + 1 == r) ? fma(-c, u.y, 0.0) : fma(-c, u.y, a.y);
+        *reinterpret_cast<double2 *>(row + j0) = a;
+    } else {
+        const double u = urow[j0];
+        row[j0] = (j0 == r) ? fma(-c, u, 0.0) : fma(-c, u, row[j0]);
+    }
+}
+
+__global__ void __launch_bounds__(256) load_f64_kernel(const double *__restrict__ A, int n, double *__restrict__ W, long long ld) {
+    const long long i = blockIdx.x;
+    const int j = blockIdx.y * 256 + threadIdx.x;
+    if (j >= ld) return;
+    W[i * ld + j] = (j < n) ? A[i * (long long)n + j] : 0.0;
+}
+
+// X[i][j] = W[i][colsrc[j]] (deferred column permutation) + isfinite scan; one CTA per row, the row staged in shared
+// memory when it fits.
+__global__ void __launch_bounds__(512) extract_f64_kernel(const double *__restrict__ W, long long ld, int n,
+                                                          const int *__restrict__ colsrc, double *__restrict__ X,
+                                                          int *__restrict__ info, int check, int staged) {
+    extern __shared__ double srow_d[];
+    const long long i = blockIdx.x;
+    const double *wr = W + i * ld;
+    double *xr = X + i * (long long)n;
+    bool bad = false;
+    if (staged) {
+        for (int j = threadIdx.x; j < n; j += 512) srow_d[j] = wr[j];
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += 512) {
+            const double v = srow_d[colsrc[j]];
+            bad |= !isfinite(v);
+            xr[j] = v;
+        }
+    } else {
+        for (int j = threadIdx.x; j < n; j += 512) {
+            const double v = wr[colsrc[j]];
+            bad |= !isfinite(v);
+            xr[j] = v;
+        }
+    }
+    if (check && __syncthreads_or(bad) && threadIdx.x == 0) atomicCAS(info, 0, -1);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+void f64_workspace_free(F64Workspace &w) {
+    cudaFree(w.W); cudaFree(w.urow); cudaFree(w.ccol); cudaFree(w.part); cudaFree(w.piv); cudaFree(w.colsrc); cudaFree(w.info);
+    cudaFree(w.io);
+    w = F64Workspace();
+}
+
+cudaError_t f64_workspace_ensure(F64Workspace &w, int n, bool with_io) {
+    if (w.n != n) {
+        f64_workspace_free(w);
+        const long long ld = ((long long)n + 1) & ~1ll;
+        cudaError_t e;
+        if ((e = cudaMalloc(&w.W, sizeof(double) * ld * n)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.urow, sizeof(double) * ld)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.ccol, sizeof(double) * ld)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.part, sizeof(PivCand) * (size_t)((n + 255) / 256))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.piv, sizeof(int) * (size_t)n)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.colsrc, sizeof(int) * (size_t)n)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.info, sizeof(int))) != cudaSuccess) return e;
+        w.n = n;
+        w.ld = ld;
+    }
+    if (with_io && !w.io) {
+        cudaError_t e = cudaMalloc(&w.io, sizeof(double) * (size_t)n * n);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// load + n x (search, swap + normalise, rank-1 update) + column permutation + extraction.  Returns the launch count.
+int f64_invert_async(F64Workspace &w, const double *A_dev, int n, double *X_dev, int nopivot, int check, cudaStream_t st) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
+        cudaFuncSetAttribute(extract_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }
+    const long long ld = w.ld;
+    int launches = 0;
+    cudaMemsetAsync(w.info, 0, sizeof(int), st);
+    load_f64_kernel<<<dim3(n, (unsigned)((ld + 255) / 256)), 256, 0, st>>>(A_dev, n, w.W, ld);
+    launches++;
+    const int nparts = (n + 255) / 256;
+    for (int r = 0; r < n; r++) {
+        if (nopivot) diag_f64_kernel<<<1, 1, 0, st>>>(w.W, ld, r, w.part);
+        else argmax_f64_kernel<<<nparts, 256, 0, st>>>(w.W, ld, n, r, r, w.part);
+        swap_normalize_f64_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.W, ld, n, r, w.part, nopivot ? 1 : nparts, w.urow, w.ccol,
+                                                                   w.piv, w.info);
+        rank1_update_f64_kernel<<<dim3((n + 63) / 64, (n + 7) / 8), dim3(32, 8), 0, st>>>(w.W, ld, n, r, w.urow, w.ccol);
+        launches += 3;
+    }
+    launch_colperm_build(w.piv, n, w.colsrc, st);
+    const size_t bytes = (size_t)n * sizeof(double);
+    const int staged = bytes <= 200 * 1024;
+    extract_f64_kernel<<<n, 512, staged ? bytes : 0, st>>>(w.W, ld, n, w.colsrc, X_dev, w.info, check, staged);
+    return launches + 2;
+}

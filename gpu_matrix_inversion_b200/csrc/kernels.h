@@ -79,4 +79,18 @@ cudaError_t launch_batched_pk(const float *A, int n, long long batch, float *X, 
 void launch_generate(float *A, int n, long long ld, u64 seed, int kind, int col0, int ncols, cudaStream_t st);
 void launch_generate_batched(float *A, int n, long long first, long long count, u64 seed0, cudaStream_t st);
 cudaError_t run_residual(const float *A, const float *X, int n, double *out_host, cudaStream_t st);
+cudaError_t run_residual_f64(const double *A, const double *X, int n, double *out_host, cudaStream_t st);
+
+// FP64 path (gj_f64.cu): unblocked in-place Gauss-Jordan, optional no-pivot mode
+struct PivCand;
+struct F64Workspace {
+    double *W = nullptr, *urow = nullptr, *ccol = nullptr, *io = nullptr;
+    PivCand *part = nullptr;
+    int *piv = nullptr, *colsrc = nullptr, *info = nullptr;
+    int n = 0;
+    long long ld = 0;
+};
+cudaError_t f64_workspace_ensure(F64Workspace &w, int n, bool with_io);
+void f64_workspace_free(F64Workspace &w);
+int f64_invert_async(F64Workspace &w, const double *A_dev, int n, double *X_dev, int nopivot, int check, cudaStream_t st);
 cudaError_t run_ffma_peak(double *tflops, cudaStream_t st);

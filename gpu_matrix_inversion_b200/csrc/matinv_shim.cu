@@ -84,6 +84,7 @@ struct Context {
     int ndev = 0;
     int device = -1;  // device the cached workspace / streams live on
     Workspace ws;
+    F64Workspace wsd;                     // FP64 path (gj_f64.cu)
     cudaStream_t stream = nullptr;
     float *hostio = nullptr;  // device staging for the host-pointer entries
     size_t hostio_bytes = 0;
@@ -130,6 +131,7 @@ void free_ws(Workspace &w) {
 
 void release_locked() {
     free_ws(g.ws);
+    f64_workspace_free(g.wsd);
     cudaFree(g.hostio); g.hostio = nullptr; g.hostio_bytes = 0;
     cudaFree(g.hostio_i); g.hostio_i = nullptr; g.hostio_i_bytes = 0;
     if (g.copy_stream) {
@@ -590,6 +592,92 @@ int matinv_residual_f32_dev(const float *A_dev, const float *X_dev, int n, doubl
     std::lock_guard<std::mutex> lk(g.mu);
     if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
     CK(run_residual(A_dev, X_dev, n, out_host, (cudaStream_t)stream));
+    return MATINV_OK;
+}
+
+static int invert_f64_locked(const double *A_dev, int n, double *X_dev, int *piv_dev, cudaStream_t st, int flags) {
+    CK(f64_workspace_ensure(g.wsd, n, false));
+    F64Workspace &w = g.wsd;
+    COUNT_LAUNCH(f64_invert_async(w, A_dev, n, X_dev, (flags & MATINV_FLAG_NOPIVOT) ? 1 : 0, !(flags & MATINV_FLAG_NOCHECK), st));
+    CK(cudaGetLastError());
+    if (piv_dev) CK(cudaMemcpyAsync(piv_dev, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    int info = 0;
+    CK(cudaMemcpyAsync(&info, w.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (info != 0) {
+        if (info > 0) snprintf(g_err, sizeof(g_err), "singular: zero or non-finite pivot at column %d", info - 1);
+        else snprintf(g_err, sizeof(g_err), "singular: non-finite entry in the inverse");
+        return MATINV_SINGULAR;
+    }
+    return MATINV_OK;
+}
+
+int matinv_invert_f64_dev(const double *A_dev, int n, double *X_dev, int *piv_dev, void *stream, int flags) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_dev || !X_dev) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    return invert_f64_locked(A_dev, n, X_dev, piv_dev, (cudaStream_t)stream, flags);
+}
+
+int matinv_invert_f64(const double *A_host, int n, double *X_host, int *piv_host, int flags) {
+    g_err[0] = 0;
+    g_t_total = g_t_compute = -1.0;
+    if (n <= 0 || !A_host || !X_host) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = ensure_stream();
+    if (rc) return rc;
+    CK(f64_workspace_ensure(g.wsd, n, true));
+    cudaStream_t st = g.stream;
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    CK(cudaMemcpyAsync(g.wsd.io, A_host, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(g.ev[0], st));
+    rc = invert_f64_locked(g.wsd.io, n, g.wsd.io, nullptr, st, flags);   // extraction reads W, so io may be overwritten
+    if (rc < 0) return rc;
+    CK(cudaEventRecord(g.ev[1], st));
+    CK(cudaMemcpyAsync(X_host, g.wsd.io, bytes, cudaMemcpyDeviceToHost, st));
+    if (piv_host) CK(cudaMemcpyAsync(piv_host, g.wsd.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+    g_t_compute = ms * 1e-3;
+    g_t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (flags & MATINV_FLAG_VERBOSE) {
+        printf("Tempo Totale Impiegato: %g seconds\n", g_t_total);
+        printf("Tempo Computazione: %g seconds\n", g_t_compute);
+        fflush(stdout);
+    }
+    return rc;
+}
+
+int matinv_residual_f64_dev(const double *A_dev, const double *X_dev, int n, double *out_host, void *stream) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_dev || !X_dev || !out_host) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    CK(run_residual_f64(A_dev, X_dev, n, out_host, (cudaStream_t)stream));
+    return MATINV_OK;
+}
+
+int matinv_host_defect_f64(const double *A_host, const double *B_host, int n, double *out_host) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_host || !B_host || !out_host) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    int rc = ensure_stream();
+    if (rc) return rc;
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    double *dA = nullptr, *dB = nullptr;
+    CK(cudaMalloc(&dA, bytes));
+    if (cudaMalloc(&dB, bytes) != cudaSuccess) { cudaFree(dA); return fail(MATINV_E_CUDA, "cudaMalloc failed"); }
+    cudaError_t e = cudaMemcpyAsync(dA, A_host, bytes, cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dB, B_host, bytes, cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) e = run_residual_f64(dA, dB, n, out_host, g.stream);
+    cudaFree(dA);
+    cudaFree(dB);
+    if (e != cudaSuccess) return fail(MATINV_E_CUDA, "%s", cudaGetErrorString(e));
     return MATINV_OK;
 }
 

@@ -35,6 +35,7 @@ extern "C" {
 #define MATINV_FLAG_UNBLOCKED 2 /* force the unblocked 3-kernel-per-column path (parity checks)  */
 #define MATINV_FLAG_VERBOSE 4   /* print the reference's two stdout lines (LIB:385-386)          */
 #define MATINV_FLAG_NOCHECK 8   /* skip the final isfinite scan (kept off the hot path timing)   */
+#define MATINV_FLAG_NOPIVOT 16  /* FP64 entries only: pivot = diagonal entry, no row interchange    */
 
 /* Replaces cl::Platform::get / getDevices (LIB:239-244).  Number of usable CUDA devices, 0 if none. */
 int matinv_device_count(void);
@@ -104,6 +105,20 @@ int matinv_generate_batched_f32_dev(float *A_dev, int n, long long first, long l
 /* ||A X - I||_F^2, ||A||_F^2, ||X||_F^2 in FP64 on the device (verification GEMM, replaces
  * SOL/matrix_multiply.cpp:15-212).  out_host[3]. */
 int matinv_residual_f32_dev(const float *A_dev, const float *X_dev, int n, double *out_host, void *stream);
+
+/* ---- FP64 entry points -------------------------------------------
+ * Device side of the development copy's double-precision functions
+ *   matrix_inversion_FP64        (/root/reference/matrix_inv_solution/matrix_inversion_solution/matrix_inversion/matrix_inversion_FP64.cpp:13)
+ *   matrix_inversion_no_pivots   (.../matrix_inversion_no_pivots.cpp:10)   -> flags |= MATINV_FLAG_NOPIVOT
+ * Same conventions as the FP32 entries (row-major, 0 ok / 1 singular or non-finite / < 0 error, piv optional).
+ * Round-1 implementation: unblocked in-place Gauss-Jordan, three launches per column, HBM-bound. */
+int matinv_invert_f64(const double *A_host, int n, double *X_host, int *piv_host, int flags);
+int matinv_invert_f64_dev(const double *A_dev, int n, double *X_dev, int *piv_dev, void *stream, int flags);
+/* FP64-input twin of matinv_residual_f32_dev with a fourth output: out_host[4] = ||AX-I||_F^2, ||A||_F^2, ||X||_F^2,
+ * ||AX||_F^2.  The C++ `matrix_multiply` (SOL/matrix_multiply.cpp:15-212: sqrt(n) - ||A B||_F) is built on it. */
+int matinv_residual_f64_dev(const double *A_dev, const double *X_dev, int n, double *out_host, void *stream);
+/* Same with host pointers (copies both operands to the device first). */
+int matinv_host_defect_f64(const double *A_host, const double *B_host, int n, double *out_host);
 
 /* Seconds spent by the last matinv_invert_f32 on this thread: total (H2D+compute+D2H, the
  * reference's "Tempo Totale") and compute ("Tempo Computazione").  Returns 0 if available. */

@@ -46,6 +46,7 @@
 
 #define GJ_NOFMA 1 /* flags bit0: a - fl(c*u) instead of fmaf(-c,u,a) */
 #define GJ_QUIRK 2 /* flags bit1 (gj_aug_f32 only): pivot search AS WRITTEN in the reference, see below */
+#define GJ_NOPIVOT 4 /* flags bit2: pivot = diagonal entry, no interchange (matrix_inversion_no_pivots.cpp:41-76) */
 
 /* The reference's pivot search exactly as its two kernels behave (LIB/mat_inv_32.cpp:61-132), for n % 256 == 0:
  * per 256-row work-group a tree reduction over the WRONG window [0, lim) of the local array with receivers
@@ -159,7 +160,7 @@ void gj_generate_hollow_f32(float *A, int n, uint32_t *state) {
             for (int j = 0; j < n; j++) M[i * ld + n + j] = (i == j) ? (T)1 : (T)0;               \
         }                                                                                         \
         for (int r = 0; r < n; r++) {                                                             \
-            int p = forced_piv ? forced_piv[r] : argmax_col_##SUF(M, ld, n, r, r);                \
+            int p = forced_piv ? forced_piv[r] : ((flags & GJ_NOPIVOT) ? r : argmax_col_##SUF(M, ld, n, r, r)); \
             T v = M[(size_t)p * ld + r];                                                          \
             QUIRK_##SUF                                                                           \
             if (piv) piv[r] = p;                                                                  \
@@ -198,7 +199,7 @@ void gj_generate_hollow_f32(float *A, int n, uint32_t *state) {
         int info = 0;                                                                             \
         if (X != A) memcpy(X, A, sizeof(T) * ld * n);                                             \
         for (int r = 0; r < n; r++) {                                                             \
-            int p = argmax_col_##SUF(X, ld, n, r, r);                                             \
+            int p = (flags & GJ_NOPIVOT) ? r : argmax_col_##SUF(X, ld, n, r, r);                  \
             T v = X[(size_t)p * ld + r];                                                          \
             piv[r] = p;                                                                           \
             if (v == (T)0 || !ISFIN(v)) { info = r + 1; break; }                                  \

@@ -23,6 +23,7 @@ _SRC = _HERE / "gj_oracle.c"
 
 NOFMA = 1
 QUIRK = 2  # gj_aug_f32 only: the reference's pivot search as written (n % 256 == 0)
+NOPIVOT = 4  # pivot = diagonal entry, no row interchange (matrix_inversion_no_pivots.cpp)
 
 SEED_UNIFORM = 0xB2000000
 SEED_DIAGDOM = 0xB2001000

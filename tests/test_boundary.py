@@ -25,6 +25,10 @@ def test_library_exports_every_declared_symbol():
     assert sorted(m.EXPORTS) == declared
     # the C++ surface: Itanium mangling of std::vector<float> matrix_inv_32(std::vector<float>, int)
     assert "_Z13matrix_inv_32St6vectorIfSaIfEEi" in exported
+    # the development copy's function set (include/matrix_inversion.h <- SOL/headers.h:5-11)
+    for sym in ("_Z21matrix_inversion_FP32St6vectorIfSaIfEEi", "_Z21matrix_inversion_FP64St6vectorIdSaIdEEi",
+                "_Z26matrix_inversion_no_pivotsSt6vectorIdSaIdEEi", "_Z15matrix_multiplySt6vectorIdSaIdEES1_"):
+        assert sym in exported, sym
 
 
 def test_python_twin_argument_conventions_without_device():
@@ -81,3 +85,63 @@ int main() {
         assert first[1] == "4" and first[2] == "0"          # inverse returned; singular -> {}
         vals = [float(x) for x in p.stdout.splitlines()[1].split()]
         assert np.allclose(vals, [0.6, -0.7, -0.2, 0.4], atol=1e-6)
+
+
+def test_fp64_surface_links_and_follows_conventions(tmp_path):
+    """include/matrix_inversion.h compiled by a caller, like a user of the reference's headers.h."""
+    src = tmp_path / "caller64.cpp"
+    src.write_text(r'''
+#include "matrix_inversion.h"
+#include <cmath>
+#include <cstdio>
+int main() {
+    std::vector<double> a = {4, 7, 2, 6};
+    int bad = 0;
+    bad |= !matrix_inversion_FP64(a, 0).empty();
+    bad |= !matrix_inversion_FP64(a, 3).empty();            // int(4/3) = 1 != 3
+    bad |= !matrix_inversion_no_pivots(a, -2).empty();
+    std::vector<double> r = matrix_inversion_FP64(a, 2);
+    std::vector<double> q = matrix_inversion_no_pivots(a, 2);
+    std::vector<double> s = matrix_inversion_FP64(std::vector<double>{1, 2, 2, 4}, 2);     // singular
+    std::vector<double> z = matrix_inversion_no_pivots(std::vector<double>{0, 1, 1, 0}, 2); // zero diagonal, no pivoting
+    std::vector<float> f = matrix_inversion_FP32(std::vector<float>{4, 7, 2, 6}, 2);
+    std::printf("%d %zu %zu %zu %zu %zu\n", bad, r.size(), q.size(), s.size(), z.size(), f.size());
+    if (r.size() == 4) {
+        std::printf("%.15f %.15f %.15f %.15f\n", r[0], r[1], r[2], r[3]);
+        std::printf("%.3e\n", matrix_multiply(r, a));
+    }
+    return bad;
+}
+''')
+    exe = tmp_path / "caller64"
+    libdir = ROOT / "gpu_matrix_inversion_b200"
+    subprocess.run(["g++", "-std=c++14", "-I", str(ROOT / "include"), str(src), "-o", str(exe), "-L", str(libdir),
+                    "-lmatinv32", f"-Wl,-rpath,{libdir}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"],
+                   check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    first = p.stdout.splitlines()[0].split()
+    assert first[0] == "0"
+    import gpu_matrix_inversion_b200 as m
+
+    if m.device_count() == 0:
+        assert first[1:] == ["0", "0", "0", "0", "0"]       # no device -> {} everywhere, never a crash
+    else:
+        assert first[1:] == ["4", "4", "0", "0", "4"]
+        vals = [float(x) for x in p.stdout.splitlines()[1].split()]
+        assert np.allclose(vals, [0.6, -0.7, -0.2, 0.4], atol=1e-14)
+        assert abs(float(p.stdout.splitlines()[2])) < 1e-12
+
+
+def test_fp64_python_twins_without_device():
+    import gpu_matrix_inversion_b200 as m
+
+    assert m.matrix_inversion_FP64(np.ones(4), 0).size == 0
+    assert m.matrix_inversion_FP64(np.ones(5), 3).size == 0
+    assert m.matrix_inversion_no_pivots(np.ones(12), 3).size == 0
+    assert np.isnan(m.matrix_multiply(np.ones(5), np.ones(5)))
+    if m.device_count() == 0:
+        assert m.matrix_inversion_FP64(np.eye(2).ravel(), 2).size == 0
+        with pytest.raises(m.MatinvError) as e:
+            m.invert_f64(np.eye(2))
+        assert e.value.code == m.E_NODEVICE

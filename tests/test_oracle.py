@@ -132,3 +132,30 @@ def test_generators_are_deterministic_and_in_range():
     assert (np.diag(H) == 0).all() and H.max() <= 9 and H.min() >= 0
     # first MSVC rand() values with seed 1: 41, 18467, 6334 -> %10 = 1, 7, 4
     assert list(H[0, 1:4]) == [1.0, 7.0, 4.0]
+
+
+def test_f64_forms_agree_and_no_pivot_mode():
+    """FP64 twins of the three formulations agree bit for bit; the no-pivot mode (matrix_inversion_no_pivots.cpp)
+    keeps the identity permutation, matches the pivoted run whenever that run never swaps, and reports a zero
+    diagonal entry as singular."""
+    rng = np.random.default_rng(64)
+    for n in (1, 2, 5, 33, 96):
+        A = rng.random((n, n)) * 100.0
+        Xa, pa, ia = o.invert_aug(A)
+        Xi, pi, ii = o.invert_inplace(A)
+        Xb, pb, ib = o.invert_blocked(A, nb=32, w=8)
+        assert ia == ii == ib == 0
+        assert np.array_equal(pa, pi) and np.array_equal(pi, pb)
+        assert np.array_equal(Xa.view(np.uint64), Xi.view(np.uint64)) or np.array_equal(Xa, Xi)
+        assert np.array_equal(Xi.view(np.uint64), Xb.view(np.uint64))
+        assert np.abs(A @ Xi - np.eye(n)).max() < 1e-8
+    D = o.generate(120, o.SEED_DIAGDOM + 120, "diagdom").astype(np.float64)
+    Xn, pn, inn = o.invert_inplace(D, flags=o.NOPIVOT)
+    Xp, pp, ip = o.invert_inplace(D)
+    assert inn == 0 and np.array_equal(pn, np.arange(120))
+    if np.array_equal(pp, np.arange(120)):
+        assert np.array_equal(Xn.view(np.uint64), Xp.view(np.uint64))
+    Xq, pq, iq = o.invert_aug(D, flags=o.NOPIVOT)
+    assert iq == 0 and np.allclose(Xq, Xn, rtol=0, atol=1e-18 + 1e-12 * np.abs(Xn).max())
+    Z = np.array([[0.0, 1.0], [1.0, 0.0]])
+    assert o.invert_inplace(Z, flags=o.NOPIVOT)[2] != 0 and o.invert_inplace(Z)[2] == 0
