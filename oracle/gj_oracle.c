@@ -45,7 +45,7 @@
 #endif
 
 #define GJ_NOFMA 1 /* flags bit0: a - fl(c*u) instead of fmaf(-c,u,a) */
-#define GJ_QUIRK 2 /* flags bit1 (gj_aug_f32 only): pivot search AS WRITTEN in the reference, see below */
+#define GJ_QUIRK 2 /* flags bit1 (gj_aug_* only): pivot search AS WRITTEN in the reference, see below */
 #define GJ_NOPIVOT 4 /* flags bit2: pivot = diagonal entry, no interchange (matrix_inversion_no_pivots.cpp:41-76) */
 
 /* The reference's pivot search exactly as its two kernels behave (LIB/mat_inv_32.cpp:61-132), for n % 256 == 0:
@@ -54,30 +54,33 @@
  * Not the parity target of the product (north_star pins the intended arg max); it exists so that the whole
  * restatement -- swap, scale, eliminate, extract -- can be compared BIT FOR BIT with outputs of the unmodified
  * reference on inputs that need real row interchanges (tests/test_oracle_vs_reference.py). */
-static int quirk_pivot_f32(const float *M, size_t ld, int n, int r, float *value) {
-    float bestv = 0.0f, besti = 0.0f;
-    const int ngroups = n / 256;
-    for (int g = 0; g < ngroups; g++) {
-        float ox = 0.0f, oy = 0.0f;
-        if (r <= g * 256 + 255) {
-            float vx[257], vy[257];
-            for (int l = 0; l < 256; l++) { vx[l] = M[(size_t)(g * 256 + l) * ld + r]; vy[l] = (float)(g * 256 + l); }
-            const int loopLimit = 256;
-            int lim = (r >= g * 256) ? loopLimit - (r % 256) : loopLimit;
-            if (lim % 2 != 0) { vx[loopLimit] = 0.0f; vy[loopLimit] = 0.0f; lim++; }
-            for (int i = lim >> 1; i > 0; i >>= 1) {
-                for (int l = 0; l < i; l++)
-                    if (fabsf(vx[l + i]) > fabsf(vx[l]) && g * 256 + l >= r) { vx[l] = vx[l + i]; vy[l] = vy[l + i]; }
-                if (i % 2 != 0 && i != 1) i++;
-            }
-            const int sel = (r >= g * 256) ? r % 256 : 0;
-            ox = vx[sel]; oy = vy[sel];
-        }
-        if (fabsf(ox) > fabsf(bestv)) { bestv = ox; besti = oy; }
+#define DEFINE_QUIRK(T, SUF, ABS)                                                                          \
+    static int quirk_pivot_##SUF(const T *M, size_t ld, int n, int r, T *value) {                          \
+        T bestv = 0, besti = 0;                                                                            \
+        const int ngroups = n / 256;                                                                       \
+        for (int g = 0; g < ngroups; g++) {                                                                \
+            T ox = 0, oy = 0;                                                                              \
+            if (r <= g * 256 + 255) {                                                                      \
+                T vx[257], vy[257];                                                                        \
+                for (int l = 0; l < 256; l++) { vx[l] = M[(size_t)(g * 256 + l) * ld + r]; vy[l] = (T)(g * 256 + l); } \
+                const int loopLimit = 256;                                                                 \
+                int lim = (r >= g * 256) ? loopLimit - (r % 256) : loopLimit;                              \
+                if (lim % 2 != 0) { vx[loopLimit] = 0; vy[loopLimit] = 0; lim++; }                         \
+                for (int i = lim >> 1; i > 0; i >>= 1) {                                                   \
+                    for (int l = 0; l < i; l++)                                                            \
+                        if (ABS(vx[l + i]) > ABS(vx[l]) && g * 256 + l >= r) { vx[l] = vx[l + i]; vy[l] = vy[l + i]; } \
+                    if (i % 2 != 0 && i != 1) i++;                                                         \
+                }                                                                                          \
+                const int sel = (r >= g * 256) ? r % 256 : 0;                                              \
+                ox = vx[sel]; oy = vy[sel];                                                                \
+            }                                                                                              \
+            if (ABS(ox) > ABS(bestv)) { bestv = ox; besti = oy; }                                          \
+        }                                                                                                  \
+        *value = bestv;                                                                                    \
+        return (int)besti;                                                                                 \
     }
-    *value = bestv;
-    return (int)besti;
-}
+DEFINE_QUIRK(float, f32, fabsf)
+DEFINE_QUIRK(double, f64, fabs) /* matrix_inversion_FP64.cpp:43-117: the same two kernels on double2 */
 
 /* ---------------------------------------------------------------- synthetic inputs (SURVEY s.8d) */
 
@@ -380,7 +383,13 @@ void gj_generate_hollow_f32(float *A, int n, uint32_t *state) {
         p = quirk_pivot_f32(M, ld, n, r, &qv);                                            \
         v = qv;                                                                           \
     }
-#define QUIRK_f64
+#define QUIRK_f64                                                                         \
+    if ((flags & GJ_QUIRK) && !forced_piv) {                                              \
+        if (n % 256 != 0) { free(M); return -2; }                                         \
+        double qv;                                                                        \
+        p = quirk_pivot_f64(M, ld, n, r, &qv);                                            \
+        v = qv;                                                                           \
+    }
 DEFINE_GJ(float, f32, fmaf, fabsf, isfinite)
 DEFINE_GJ(double, f64, fma, fabs, isfinite)
 

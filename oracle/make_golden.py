@@ -37,25 +37,35 @@ def make_input(family: str, n: int, mod: str) -> np.ndarray:
         A[9] = A[5]
     elif mod == "zero_col11":
         A[:, 11] = 0.0
+    elif mod == "zero_diag3":
+        A[3, 3] = 0.0
     elif mod != "none":
         raise ValueError(mod)
     return A
 
 
+def make_input64(family: str, n: int, mod: str) -> np.ndarray:
+    """FP64 fixtures: the FP32 workload widened (exactly representable), so the same generators serve both."""
+    return make_input(family, n, mod).astype(np.float64)
+
+
 def run_reference(fn_name: str, A: np.ndarray, contract: str):
-    """Runs in a child process: the kernel build mode is read from the environment when the program is built."""
+    """Runs in a child process: the kernel build mode is read from the environment when the program is built.
+    Works for both element types (the bridge takes untyped pointers).  matrix_inversion_no_pivots enqueues its row and
+    column kernels over n+1 work-items with a local size of 256 (matrix_inversion_no_pivots.cpp:507): invalid in
+    OpenCL 1.2, accepted by drivers that allow a ragged last group -- minicl follows the latter with MINICL_RAGGED=1."""
     code = f"""
 import ctypes, numpy as np, sys
 L = ctypes.CDLL({str(REF)!r})
-fp = ctypes.POINTER(ctypes.c_float)
-f = getattr(L, {fn_name!r}); f.argtypes = [fp, ctypes.c_longlong, ctypes.c_int, fp]
+f = getattr(L, {fn_name!r}); f.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]
 A = np.load(sys.argv[1]); n = A.shape[0]; X = np.zeros_like(A)
-rc = f(A.ctypes.data_as(fp), A.size, n, X.ctypes.data_as(fp))
+rc = f(A.ctypes.data, A.size, n, X.ctypes.data)
 np.save(sys.argv[2], X); open(sys.argv[3], 'w').write(str(rc))
 """
     tmp = Path("/tmp/minicl_golden"); tmp.mkdir(exist_ok=True)
     np.save(tmp / "a.npy", A)
-    env = dict(os.environ, MINICL_FP_CONTRACT=contract, MINICL_CACHE=str(ROOT / "oracle" / "_ref" / "kcache"))
+    env = dict(os.environ, MINICL_FP_CONTRACT=contract, MINICL_CACHE=str(ROOT / "oracle" / "_ref" / "kcache"),
+               MINICL_RAGGED="1" if "no_pivots" in fn_name else "0")
     subprocess.run([sys.executable, "-c", code, str(tmp / "a.npy"), str(tmp / "x.npy"), str(tmp / "rc.txt")], env=env, check=True,
                    stdout=subprocess.DEVNULL)
     return int((tmp / "rc.txt").read_text()), np.load(tmp / "x.npy")
@@ -77,6 +87,19 @@ FIXTURES = [
     ("sol_zero_col11", "ref_matrix_inversion_FP32", "uniform", 256, "zero_col11", "off"),
 ]
 
+# FP64 entry points of the development copy; outputs stored as SHA-256 only
+FIXTURES64 = [
+    ("sol64_uniform256_off", "ref_matrix_inversion_FP64", "uniform", 256, "none", "off"),
+    ("sol64_uniform256_fast", "ref_matrix_inversion_FP64", "uniform", 256, "none", "fast"),
+    ("sol64_hollow512_off", "ref_matrix_inversion_FP64", "hollow", 512, "none", "off"),
+    ("sol64_zero_row7", "ref_matrix_inversion_FP64", "uniform", 256, "zero_row7", "off"),
+    ("sol64_nan00", "ref_matrix_inversion_FP64", "uniform", 256, "nan00", "off"),
+    ("nopiv_diagdom256_off", "ref_matrix_inversion_no_pivots", "diagdom", 256, "none", "off"),
+    ("nopiv_diagdom512_fast", "ref_matrix_inversion_no_pivots", "diagdom", 512, "none", "fast"),
+    ("nopiv_uniform256_off", "ref_matrix_inversion_no_pivots", "uniform", 256, "none", "off"),
+    ("nopiv_zero_diag3", "ref_matrix_inversion_no_pivots", "diagdom", 256, "zero_diag3", "off"),
+]
+
 if __name__ == "__main__":
     assert REF.exists(), "build the reference first: make -C oracle -f Makefile.ref"
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -88,3 +111,11 @@ if __name__ == "__main__":
         np.savez_compressed(GOLD / f"ref_{name}.npz", fn=fn, family=family, n=n, mod=mod, contract=contract, rc=rc, sha256=sha,
                             X=store, finite=bool(np.isfinite(X).all()) if rc == 0 else False)
         print(f"{name:24s} rc={rc} finite={np.isfinite(X).all() if rc == 0 else '-'} sha={sha[:16]}")
+    for name, fn, family, n, mod, contract in FIXTURES64:
+        A = make_input64(family, n, mod)
+        rc, X = run_reference(fn, A, contract)
+        finite = bool(np.isfinite(X).all()) if rc == 0 else False
+        sha = hashlib.sha256(np.ascontiguousarray(X).tobytes()).hexdigest() if rc == 0 else ""
+        np.savez_compressed(GOLD / f"ref_{name}.npz", fn=fn, family=family, n=n, mod=mod, contract=contract, rc=rc, sha256=sha,
+                            finite=finite)
+        print(f"{name:24s} rc={rc} finite={finite if rc == 0 else '-'} sha={sha[:16]}")

@@ -195,17 +195,23 @@ cl_int clBuildProgram(cl_program p, cl_uint, const cl_device_id *, const char *,
     }
     const char *mode = getenv("MINICL_FP_CONTRACT");
     const std::string contract = (mode && std::string(mode) == "fast") ? "fast" : "off";
-    const std::string full = std::string("#include \"") + MINICL_PRELUDE + "\"\n" + body + "\n" + wrappers;
+    // __local arrays are thread-local statics of the kernel module.  The reference's maxPivotKernel writes one element past
+    // the end of its 256-entry __local array when the search window has odd length (localData2[loopLimit], loopLimit = 256):
+    // harmless in a GPU's local memory, heap corruption in a TLS block that ends exactly there -- so the module's TLS
+    // block is fenced with slack on both sides.
+    const std::string guard_head = "static __thread char minicl_tls_head[4096] __attribute__((used));\n";
+    const std::string guard_tail = "static __thread char minicl_tls_tail[4096] __attribute__((used));\n";
+    const std::string full = std::string("#include \"") + MINICL_PRELUDE + "\"\n" + guard_head + body + "\n" + guard_tail + wrappers;
     const char *cd = getenv("MINICL_CACHE");
     const std::string cache = cd ? cd : "/tmp/minicl_cache";
     mkdir(cache.c_str(), 0755);
     char name[64];
-    snprintf(name, sizeof(name), "%016llx", (unsigned long long)fnv(full + contract + "v3"));
+    snprintf(name, sizeof(name), "%016llx", (unsigned long long)fnv(full + contract + "v4"));
     const std::string so = cache + "/k" + name + ".so", cfile = cache + "/k" + name + ".c";
     if (access(so.c_str(), R_OK) != 0) {
         { std::ofstream f(cfile); f << full; }
         const std::string tmp = so + "." + std::to_string(getpid());
-        const std::string cmd = "gcc -x c -std=gnu11 -O2 -mfma -ffp-contract=" + contract + " -w -shared -fPIC -o " + tmp + " " + cfile +
+        const std::string cmd = "gcc -x c -std=gnu11 -O2 -mfma -fno-toplevel-reorder -ffp-contract=" + contract + " -w -shared -fPIC -o " + tmp + " " + cfile +
                                 " -lm 2> " + cfile + ".log";
         if (system(cmd.c_str()) != 0) {
             std::ifstream lf(cfile + ".log");

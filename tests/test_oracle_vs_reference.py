@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from oracle import gj_oracle as o
-from oracle.make_golden import FIXTURES, GOLD, REF, make_input
+from oracle.make_golden import FIXTURES, FIXTURES64, GOLD, REF, make_input, make_input64
 
 NAMES = [f[0] for f in FIXTURES]
 
@@ -37,6 +37,26 @@ def test_oracle_reproduces_reference_output(name):
         assert hashlib.sha256(X.tobytes()).hexdigest() == str(g["sha256"])
         if g["X"].size:
             assert np.array_equal(bits(X), bits(g["X"]))
+
+
+@pytest.mark.parametrize("name", [f[0] for f in FIXTURES64])
+def test_oracle_reproduces_reference_fp64_and_no_pivot_output(name):
+    """matrix_inversion_FP64.cpp (same as-written pivot search, on double2) and matrix_inversion_no_pivots.cpp
+    (pivot = diagonal entry) executed unmodified; the FP64 oracle must give the same bytes and the same verdicts."""
+    g = np.load(GOLD / f"ref_{name}.npz")
+    n, rc = int(g["n"]), int(g["rc"])
+    A = make_input64(str(g["family"]), n, str(g["mod"]))
+    mode = o.NOPIVOT if "no_pivots" in str(g["fn"]) else o.QUIRK
+    X, piv, info = o.invert_aug(A, flags=mode | (o.NOFMA if str(g["contract"]) == "off" else 0))
+    assert (info != 0) == (rc == 1), f"singular verdict differs: oracle info={info}, reference rc={rc}"
+    if rc == 0:
+        assert X.dtype == np.float64
+        assert hashlib.sha256(X.tobytes()).hexdigest() == str(g["sha256"])
+        if mode == o.NOPIVOT:
+            assert np.array_equal(piv, np.arange(n))
+            # the in-place form the CUDA path implements is the same arithmetic (only the sign of exact zeros may differ)
+            Xi, _, ii = o.invert_inplace(A, flags=mode | (o.NOFMA if str(g["contract"]) == "off" else 0))
+            assert ii == 0 and np.array_equal(Xi, X)
 
 
 def test_shipped_and_dev_copy_agree():
