@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline measurement of the hot path (see the contract in DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload n16384|n4096|batched64|n65536]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload n16384|n4096|n32768|batched64|n65536|fp64_n4096]
     python bench.py --impl reference ...      # the reference's own CPU path on the host cores
 
 A "step" is one pass of the hot path over one batch of synthetic input:
@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="n16384", choices=["n16384", "n4096", "n32768", "batched64", "n65536"])
+    ap.add_argument("--workload", default="n16384", choices=["n16384", "n4096", "n32768", "batched64", "n65536", "fp64_n4096"])
     ap.add_argument("--kind", default="uniform", choices=["uniform", "diagdom"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="batched64: matrices per GPU")
     ap.add_argument("--order", type=int, default=0, help="n65536: override the order (e.g. 16384 for a quick sharded run)")
@@ -162,7 +162,7 @@ def run_reference(args):
         os.environ[var] = str(os.cpu_count() or 1)
     import numpy as np
 
-    n_target = {"n16384": 16384, "n4096": 4096, "n32768": 32768, "n65536": 65536, "batched64": 64}[args.workload]
+    n_target = {"n16384": 16384, "n4096": 4096, "n32768": 32768, "n65536": 65536, "batched64": 64, "fp64_n4096": 4096}[args.workload]
     cores = os.cpu_count() or 1
     if args.workload == "batched64":
         B = 65536
@@ -305,6 +305,68 @@ def main():
                   "n": n, "nb": 128, "l2": "inputs_larger_than_l2" if n >= 8192 else "l2_resident_input",
                   "parallelism": f"replicas_x{world}" if world > 1 else "single_gpu"}
         unit, scaling = "GFLOP/s", "weak"
+    elif args.workload == "fp64_n4096":
+        # FP64 entry point (matrix_inversion_FP64): unblocked path, the rank-1 update streams the matrix once per column
+        n = 4096
+        gen = torch.Generator(device="cuda").manual_seed(0xB2006400 + rank)
+        A = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=gen) * 100.0
+        X = torch.empty_like(A)
+        for _ in range(W):
+            rc, _ = m.invert_f64_dev(A, X)
+            assert rc == m.OK, m.last_error()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sampler.start()
+        ev0.record()
+        for _ in range(K):
+            rc, _ = m.invert_f64_dev(A, X)
+        ev1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        barrier()
+        assert rc == m.OK
+        # kernel-level pass: one more inversion with an event pair around each of its 4096 rank-1 updates (kept out of the
+        # timed loop: 8192 event records would cost the step about 7 %)
+        m.profile_enable(True)
+        rc, _ = m.invert_f64_dev(A, X)
+        torch.cuda.synchronize()
+        prof = m.profile_read()
+        m.profile_enable(False)
+        ms = max_over_ranks(ev0.elapsed_time(ev1) / K)
+        flops = 2.0 * n ** 3
+        value = world * flops / (ms * 1e-3) / 1e9
+        R = A @ X - torch.eye(n, dtype=torch.float64, device="cuda")
+        extra["residual"] = float(R.norm() / (n * A.norm() * X.norm()))
+        Ah = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        Xh = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        Ah.copy_(A)
+        torch.cuda.synchronize()
+        rc = m.lib.matinv_invert_f64(Ah.data_ptr(), n, Xh.data_ptr(), None, 0)
+        assert rc == m.OK, m.last_error()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            rc = m.lib.matinv_invert_f64(Ah.data_ptr(), n, Xh.data_ptr(), None, 0)
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / K)
+        e2e = {"value": world * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n * n,
+               "d2h_bytes_per_step": 8 * n * n, "ms_per_step": e2e_s * 1e3,
+               "api": "matinv_invert_f64 (what matrix_inversion_FP64 calls), pinned host buffers"}
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        k_ms = prof["gemm_ms"] / max(prof["gemm_launches"], 1)          # the hooks bracket the rank-1 updates on this path
+        gbs = 16.0 * n * n / (k_ms * 1e-3) / 1e9 if k_ms else 0.0       # read + write of the n x n doubles per launch
+        roofline = {"bound": "hbm", "kernel": "rank1_update_f64_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                    "frac": gbs / hbm, "traffic": None,
+                    "traffic_note": "algorithmic bytes per launch 16 n^2 = 2.68e8; the 134 MB matrix is about the size of L2 "
+                                    "(126 MB), so part of it is served from L2 at this order",
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                    "kernel_share_of_step": prof["gemm_ms"] / ms}
+        launches = prof["launches"] * K
+        config = {"workload": f"N={n} U(0,100) FP64 single inversion per GPU, partial pivoting (matrix_inversion_FP64)",
+                  "n": n, "l2": "input_about_l2_size", "parallelism": f"replicas_x{world}" if world > 1 else "single_gpu",
+                  "path": "unblocked, three launches per column"}
+        unit, scaling = "GFLOP/s", "weak"
     elif args.workload == "batched64":
         n, batch = 64, args.batch
         A = m.generate_batched_dev(n, rank * batch, batch, SEED_BATCHED)
@@ -407,12 +469,13 @@ def main():
         backend.close()
 
     line = {"metric": METRIC, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f64" if args.workload == "fp64_n4096" else "f32",
             "data": "synthetic", "config": config, "roofline": roofline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks}
     line.update(extra)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(16384 if args.workload != "n4096" else 4096)
+        line["cpu_baseline"] = cpu_baseline(4096 if args.workload in ("n4096", "fp64_n4096") else 16384)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -92,5 +92,6 @@ struct F64Workspace {
 };
 cudaError_t f64_workspace_ensure(F64Workspace &w, int n, bool with_io);
 void f64_workspace_free(F64Workspace &w);
-int f64_invert_async(F64Workspace &w, const double *A_dev, int n, double *X_dev, int nopivot, int check, cudaStream_t st);
+int f64_invert_async(F64Workspace &w, const double *A_dev, int n, double *X_dev, int nopivot, int check, cudaStream_t st,
+                     cudaEvent_t (*prof_event)());
 cudaError_t run_ffma_peak(double *tflops, cudaStream_t st);
