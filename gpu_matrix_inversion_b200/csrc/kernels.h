@@ -85,6 +85,7 @@ cudaError_t run_residual_f64(const double *A, const double *X, int n, double *ou
 struct PivCand;
 struct F64Workspace {
     double *W = nullptr, *urow = nullptr, *ccol = nullptr, *io = nullptr;
+    double *CT = nullptr, *U = nullptr, *pv = nullptr, *upan = nullptr;   // blocked schedule: multipliers (transposed), snapshots
     PivCand *part = nullptr;
     int *piv = nullptr, *colsrc = nullptr, *info = nullptr;
     int n = 0;
@@ -94,4 +95,6 @@ cudaError_t f64_workspace_ensure(F64Workspace &w, int n, bool with_io);
 void f64_workspace_free(F64Workspace &w);
 int f64_invert_async(F64Workspace &w, const double *A_dev, int n, double *X_dev, int nopivot, int check, cudaStream_t st,
                      cudaEvent_t (*prof_event)());
+int f64_invert_blocked_async(F64Workspace &w, const double *A_dev, int n, double *X_dev, int nopivot, int check, cudaStream_t st,
+                             cudaEvent_t (*prof_event)());
 cudaError_t run_ffma_peak(double *tflops, cudaStream_t st);

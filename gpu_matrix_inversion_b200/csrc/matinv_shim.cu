@@ -598,9 +598,14 @@ int matinv_residual_f32_dev(const float *A_dev, const float *X_dev, int n, doubl
 static int invert_f64_locked(const double *A_dev, int n, double *X_dev, int *piv_dev, cudaStream_t st, int flags) {
     CK(f64_workspace_ensure(g.wsd, n, false));
     F64Workspace &w = g.wsd;
-    COUNT_LAUNCH(f64_invert_async(w, A_dev, n, X_dev, (flags & MATINV_FLAG_NOPIVOT) ? 1 : 0, !(flags & MATINV_FLAG_NOCHECK), st,
-                                  g_prof.on ? prof_event : nullptr));
-    if (g_prof.on) g_prof.gemm_flops += 2.0 * (double)n * (double)(n - 1) * (double)n;   // n rank-1 updates of (n-1) x n FMAs
+    const int nopiv = (flags & MATINV_FLAG_NOPIVOT) ? 1 : 0, check = !(flags & MATINV_FLAG_NOCHECK);
+    if (flags & MATINV_FLAG_UNBLOCKED) {
+        COUNT_LAUNCH(f64_invert_async(w, A_dev, n, X_dev, nopiv, check, st, g_prof.on ? prof_event : nullptr));
+        if (g_prof.on) g_prof.gemm_flops += 2.0 * (double)n * (double)(n - 1) * (double)n;   // n rank-1 updates of (n-1) x n FMAs
+    } else {
+        COUNT_LAUNCH(f64_invert_blocked_async(w, A_dev, n, X_dev, nopiv, check, st, g_prof.on ? prof_event : nullptr));
+        if (g_prof.on) g_prof.gemm_flops += 2.0 * (double)(n - 64) * (double)(n - 64) * (double)n;   // trailing updates
+    }
     CK(cudaGetLastError());
     if (piv_dev) CK(cudaMemcpyAsync(piv_dev, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
     int info = 0;

@@ -116,3 +116,20 @@ def test_f64_residual_at_n2048(m):
     assert rel <= 1e-13
     rc, A2 = m.invert_f64_dev(X)
     assert rc == m.OK and float((A2 - A).abs().max() / A.abs().max()) <= 1e-7
+
+
+@pytest.mark.parametrize("n", [63, 64, 65, 130, 777, 1500])
+def test_f64_blocked_equals_unblocked(m, n):
+    """The default (blocked, 64-column panels) and the unblocked schedule are the same arithmetic in a different order of
+    independent operations: same bytes, with and without pivoting."""
+    A = uniform64(n, 9100 + n)
+    Xb, pb = m.invert_f64(A, want_piv=True)
+    Xu, pu = m.invert_f64(A, want_piv=True, flags=m.FLAG_UNBLOCKED)
+    assert Xb is not None and np.array_equal(pb, pu) and np.array_equal(bits(Xb), bits(Xu))
+    D = A + np.eye(n) * 100.0 * n
+    Db = m.invert_f64(D, nopivot=True)
+    Du = m.invert_f64(D, nopivot=True, flags=m.FLAG_UNBLOCKED)
+    assert np.array_equal(bits(Db), bits(Du))
+    if n <= 777:
+        Xo, po, io = o.invert_inplace(A)
+        assert io == 0 and np.array_equal(pu, po) and np.array_equal(bits(Xu), bits(Xo))
