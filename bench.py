@@ -306,7 +306,7 @@ def main():
                   "parallelism": f"replicas_x{world}" if world > 1 else "single_gpu"}
         unit, scaling = "GFLOP/s", "weak"
     elif args.workload == "fp64_n4096":
-        # FP64 entry point (matrix_inversion_FP64): unblocked path, the rank-1 update streams the matrix once per column
+        # FP64 entry point (matrix_inversion_FP64), blocked schedule of gj_f64.cu
         n = 4096
         gen = torch.Generator(device="cuda").manual_seed(0xB2006400 + rank)
         A = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=gen) * 100.0
@@ -325,8 +325,7 @@ def main():
         clocks = sampler.stop()
         barrier()
         assert rc == m.OK
-        # kernel-level pass: one more inversion with an event pair around each of its 4096 rank-1 updates (kept out of the
-        # timed loop: 8192 event records would cost the step about 7 %)
+        # kernel-level pass: one more inversion with an event pair around each trailing update
         m.profile_enable(True)
         rc, _ = m.invert_f64_dev(A, X)
         torch.cuda.synchronize()
@@ -354,18 +353,24 @@ def main():
                "api": "matinv_invert_f64 (what matrix_inversion_FP64 calls), pinned host buffers"}
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
         hbm = peaks.get("hbm_gbs", 6650.0)
-        k_ms = prof["gemm_ms"] / max(prof["gemm_launches"], 1)          # the hooks bracket the rank-1 updates on this path
-        gbs = 16.0 * n * n / (k_ms * 1e-3) / 1e9 if k_ms else 0.0       # read + write of the n x n doubles per launch
-        roofline = {"bound": "hbm", "kernel": "rank1_update_f64_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+        # the hooks bracket the trailing updates of the blocked schedule: per launch (n-64)^2 doubles read + written and
+        # 2 (n-64)^2 64 flop; both ceilings are reported because at 64-wide panels the kernel sits near the ridge
+        k_ms = prof["gemm_ms"] / max(prof["gemm_launches"], 1)
+        mrows = float(n - 64)
+        gbs = 16.0 * mrows * mrows / (k_ms * 1e-3) / 1e9 if k_ms else 0.0
+        tfl = 2.0 * mrows * mrows * 64 / (k_ms * 1e-3) / 1e12 if k_ms else 0.0
+        fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+        roofline = {"bound": "hbm", "kernel": "trailing_f64_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s",
                     "frac": gbs / hbm, "traffic": None,
-                    "traffic_note": "algorithmic bytes per launch 16 n^2 = 2.68e8; the 134 MB matrix is about the size of L2 "
-                                    "(126 MB), so part of it is served from L2 at this order",
+                    "traffic_note": "algorithmic bytes per launch 16 (n-64)^2 = 2.60e8 (the 134 MB matrix is about the size of "
+                                    "L2, so part of it is served from L2 at this order)",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                    "fp64_tflops": tfl, "fp64_frac_of_nominal": tfl / fp64_nominal, "fp64_nominal_peak_tflops": fp64_nominal,
                     "kernel_share_of_step": prof["gemm_ms"] / ms}
         launches = prof["launches"] * K
         config = {"workload": f"N={n} U(0,100) FP64 single inversion per GPU, partial pivoting (matrix_inversion_FP64)",
                   "n": n, "l2": "input_about_l2_size", "parallelism": f"replicas_x{world}" if world > 1 else "single_gpu",
-                  "path": "unblocked, three launches per column"}
+                  "path": "blocked, 64-column panels (two launches per column + recurrence + trailing update per panel)"}
         unit, scaling = "GFLOP/s", "weak"
     elif args.workload == "batched64":
         n, batch = 64, args.batch

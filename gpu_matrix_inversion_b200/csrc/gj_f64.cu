@@ -42,11 +42,12 @@ __device__ __forceinline__ void warp_best(u64 &mag, int &row, double &val) {
 // CTA-wide best of (mag,row,val); valid in every thread of warp 0 afterwards (sm: 8 entries each)
 __device__ __forceinline__ void block_best(u64 &mag, int &row, double &val, u64 *smag, int *srow, double *sval) {
     warp_best(mag, row, val);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lin = threadIdx.y * blockDim.x + threadIdx.x;   // 1-D blocks and (32, 8) blocks alike
+    const int lane = lin & 31, warp = lin >> 5;
     if (lane == 0) { smag[warp] = mag; srow[warp] = row; sval[warp] = val; }
     __syncthreads();
     if (warp == 0) {
-        const int nw = blockDim.x >> 5;
+        const int nw = (blockDim.x * blockDim.y) >> 5;
         mag = (lane < nw) ? smag[lane] : 0ull;
         row = (lane < nw) ? srow[lane] : 0x7FFFFFFF;
         val = (lane < nw) ? sval[lane] : 0.0;
@@ -247,20 +248,43 @@ __global__ void __launch_bounds__(256) panel_pivot_f64_kernel(double *__restrict
     }
 }
 
-// (3b) rank-1 update restricted to the panel's columns: one warp per row, two columns per lane
+// (3b) rank-1 update restricted to the panel's columns: one warp per row, two columns per lane.  With `next_part` the
+// kernel also leaves the arg-max partials of the NEXT column (r+1, rows > r) -- one per CTA of 8 rows -- so that the
+// following pivot step needs no search launch of its own (the first column of a panel still does: the trailing
+// update has just rewritten it).
 __global__ void __launch_bounds__(256) panel_rank1_f64_kernel(double *__restrict__ W, long long ld, int n, int r, int k0, int kw,
                                                               int t, const double *__restrict__ CT,
-                                                              const double *__restrict__ upan) {
+                                                              const double *__restrict__ upan,
+                                                              PivCand *__restrict__ next_part) {
+    __shared__ u64 smag[8];
+    __shared__ int srow[8];
+    __shared__ double sval[8];
     const int i = blockIdx.x * 8 + threadIdx.y;
-    if (i >= n || i == r) return;
-    const double c = CT[(long long)t * ld + i];
-    double *row = W + (long long)i * ld + k0;
+    const bool active = i < n && i != r;
+    u64 mag = 0;
+    int row = 0x7FFFFFFF;
+    double val = 0.0;
+    if (active) {
+        const double c = CT[(long long)t * ld + i];
+        double *wr = W + (long long)i * ld + k0;
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int jj = 2 * threadIdx.x + q;
-        if (jj >= kw) break;
-        const double u = upan[jj];
-        row[jj] = (k0 + jj == r) ? fma(-c, u, 0.0) : fma(-c, u, row[jj]);
+        for (int q = 0; q < 2; q++) {
+            const int jj = 2 * threadIdx.x + q;
+            if (jj < kw) {
+                const double u = upan[jj];
+                const double a = (k0 + jj == r) ? fma(-c, u, 0.0) : fma(-c, u, wr[jj]);
+                wr[jj] = a;
+                if (next_part && jj == t + 1 && i > r) { val = a; mag = gj_mag64(a, i == r + 1); row = i; }
+            }
+        }
+    }
+    if (next_part) {   // uniform across the CTA
+        block_best(mag, row, val, smag, srow, sval);
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            PivCand c;
+            c.mag = mag; c.val = val; c.row = row; c.pad = 0;
+            next_part[blockIdx.x] = c;
+        }
     }
 }
 
@@ -299,53 +323,82 @@ __global__ void __launch_bounds__(128) rowblock_f64_kernel(double *__restrict__ 
     for (int t = 0; t < kw; t++) W[(long long)(k0 + t) * ld + j] = s.x[t][tid];
 }
 
-// (5) trailing update, 64 x 64 tiles, 256 threads x (4 x 4); the tile row of the pivot rows and the tile column of the
-// panel are skipped (k0 is a multiple of 64).  Accumulators are seeded from W and take the kw FMAs in step order.
+// (5) trailing update: 128 x 64 tiles, 256 threads x (8 x 4) doubles; the tile column of the panel is skipped (k0 is a
+// multiple of 64), the pivot rows are computed along and not stored.  Accumulators are seeded from W and take the kw
+// FMAs in step order.  The whole K extent (kw <= 64) of both operands sits in shared memory: 96 KB, two CTAs per SM.
 struct F64GemmSmem {
-    double a[F64_NB][64];   // a[t][ii] = CT[t][i0 + ii]
-    double b[F64_NB][64];   // b[t][jj] = U[t][j0 + jj]
+    double a[F64_NB][128];   // a[t][ii] = CT[t][i0 + ii]
+    double b[F64_NB][64];    // b[t][jj] = U[t][j0 + jj]
 };
 
-__global__ void __launch_bounds__(256) trailing_f64_kernel(double *__restrict__ W, long long ld, int n, int k0, int kw,
-                                                           const double *__restrict__ CT, const double *__restrict__ U) {
+__global__ void __launch_bounds__(256, 2) trailing_f64_kernel(double *__restrict__ W, long long ld, int n, int k0, int kw,
+                                                              const double *__restrict__ CT, const double *__restrict__ U) {
     extern __shared__ __align__(16) unsigned char f64_smem[];
     F64GemmSmem &s = *reinterpret_cast<F64GemmSmem *>(f64_smem);
     const int skip = k0 / 64;
-    int tj = blockIdx.x, ti = blockIdx.y;
+    int tj = blockIdx.x;
     tj += (tj >= skip);
-    ti += (ti >= skip);
-    const int i0 = ti * 64, j0 = tj * 64;
+    const int i0 = blockIdx.y * 128, j0 = tj * 64;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int e = tid; e < kw * 128; e += 256) {
+        const int t = e >> 7, c = e & 127;
+        s.a[t][c] = (i0 + c < n) ? CT[(long long)t * ld + i0 + c] : 0.0;
+    }
     for (int e = tid; e < kw * 64; e += 256) {
         const int t = e >> 6, c = e & 63;
-        s.a[t][c] = (i0 + c < n) ? CT[(long long)t * ld + i0 + c] : 0.0;
         s.b[t][c] = (j0 + c < n) ? U[(long long)t * ld + j0 + c] : 0.0;
     }
-    double acc[4][4];
+    double acc[8][4];
+    const bool full = (i0 + 128 <= n) && (j0 + 64 <= n);
 #pragma unroll
-    for (int q = 0; q < 4; q++)
+    for (int q = 0; q < 8; q++) {
+        const int i = i0 + ty * 8 + q;
+        if (full) {
+            const double2 c0 = *reinterpret_cast<const double2 *>(W + (long long)i * ld + j0 + tx * 4);
+            const double2 c1 = *reinterpret_cast<const double2 *>(W + (long long)i * ld + j0 + tx * 4 + 2);
+            acc[q][0] = c0.x; acc[q][1] = c0.y; acc[q][2] = c1.x; acc[q][3] = c1.y;
+        } else {
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            const int i = i0 + ty * 4 + q, j = j0 + tx * 4 + w;
-            acc[q][w] = (i < n && j < n) ? W[(long long)i * ld + j] : 0.0;
+            for (int w = 0; w < 4; w++) {
+                const int j = j0 + tx * 4 + w;
+                acc[q][w] = (i < n && j < n) ? W[(long long)i * ld + j] : 0.0;
+            }
         }
+    }
     __syncthreads();
+#pragma unroll 4
     for (int t = 0; t < kw; t++) {
-        double a[4], b[4];
+        double a[8], b[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) { a[q] = s.a[t][ty * 4 + q]; b[q] = s.b[t][tx * 4 + q]; }
+        for (int q = 0; q < 8; q += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(&s.a[t][ty * 8 + q]);
+            a[q] = v.x; a[q + 1] = v.y;
+        }
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int w = 0; w < 4; w += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(&s.b[t][tx * 4 + w]);
+            b[w] = v.x; b[w + 1] = v.y;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++)
 #pragma unroll
             for (int w = 0; w < 4; w++) acc[q][w] = fma(-a[q], b[w], acc[q][w]);
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++)
+    for (int q = 0; q < 8; q++) {
+        const int i = i0 + ty * 8 + q;
+        if (i >= k0 && i < k0 + kw) continue;   // pivot rows: brought up to date by the recurrence kernel
+        if (full) {
+            *reinterpret_cast<double2 *>(W + (long long)i * ld + j0 + tx * 4) = make_double2(acc[q][0], acc[q][1]);
+            *reinterpret_cast<double2 *>(W + (long long)i * ld + j0 + tx * 4 + 2) = make_double2(acc[q][2], acc[q][3]);
+        } else {
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            const int i = i0 + ty * 4 + q, j = j0 + tx * 4 + w;
-            if (i < n && j < n) W[(long long)i * ld + j] = acc[q][w];
+            for (int w = 0; w < 4; w++) {
+                const int j = j0 + tx * 4 + w;
+                if (i < n && j < n) W[(long long)i * ld + j] = acc[q][w];
+            }
         }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -363,7 +416,7 @@ cudaError_t f64_workspace_ensure(F64Workspace &w, int n, bool with_io) {
         if ((e = cudaMalloc(&w.W, sizeof(double) * ld * n)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.urow, sizeof(double) * ld)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.ccol, sizeof(double) * ld)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&w.part, sizeof(PivCand) * (size_t)((n + 255) / 256))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.part, sizeof(PivCand) * (size_t)((n + 7) / 8 + 1))) != cudaSuccess) return e;   // one per 8 rows (fused search)
         if ((e = cudaMalloc(&w.piv, sizeof(int) * (size_t)n)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.colsrc, sizeof(int) * (size_t)n)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.info, sizeof(int))) != cudaSuccess) return e;
@@ -400,19 +453,23 @@ int f64_invert_blocked_async(F64Workspace &w, const double *A_dev, int n, double
     const int ntile = (n + 63) / 64;
     for (int k0 = 0; k0 < n; k0 += F64_NB) {
         const int kw = (n - k0 < F64_NB) ? n - k0 : F64_NB;
+        const int nrow8 = (n + 7) / 8;
         for (int t = 0; t < kw; t++) {
             const int r = k0 + t;
-            if (nopivot) diag_f64_kernel<<<1, 1, 0, st>>>(w.W, ld, r, w.part);
-            else argmax_f64_kernel<<<nparts, 256, 0, st>>>(w.W, ld, n, r, r, w.part);
-            panel_pivot_f64_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.W, ld, n, r, k0, kw, t, w.part, nopivot ? 1 : nparts, w.CT,
-                                                                    w.upan, w.pv, w.piv, w.info);
-            panel_rank1_f64_kernel<<<(n + 7) / 8, dim3(32, 8), 0, st>>>(w.W, ld, n, r, k0, kw, t, w.CT, w.upan);
-            launches += 3;
+            // the search: fused into the previous step's panel update except for the first column of a panel
+            int np = nrow8;
+            if (nopivot) { diag_f64_kernel<<<1, 1, 0, st>>>(w.W, ld, r, w.part); np = 1; launches++; }
+            else if (t == 0) { argmax_f64_kernel<<<nparts, 256, 0, st>>>(w.W, ld, n, r, r, w.part); np = nparts; launches++; }
+            panel_pivot_f64_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.W, ld, n, r, k0, kw, t, w.part, np, w.CT, w.upan, w.pv,
+                                                                    w.piv, w.info);
+            const bool fuse = !nopivot && t + 1 < kw;
+            panel_rank1_f64_kernel<<<nrow8, dim3(32, 8), 0, st>>>(w.W, ld, n, r, k0, kw, t, w.CT, w.upan, fuse ? w.part : nullptr);
+            launches += 2;
         }
         if (n > kw) {
             rowblock_f64_kernel<<<(n + 127) / 128, 128, sizeof(F64RowblockSmem), st>>>(w.W, ld, n, k0, kw, w.CT, w.pv, w.U);
             if (prof_event) cudaEventRecord(prof_event(), st);
-            trailing_f64_kernel<<<dim3(ntile - 1, ntile - 1), 256, sizeof(F64GemmSmem), st>>>(w.W, ld, n, k0, kw, w.CT, w.U);
+            trailing_f64_kernel<<<dim3(ntile - 1, (n + 127) / 128), 256, sizeof(F64GemmSmem), st>>>(w.W, ld, n, k0, kw, w.CT, w.U);
             if (prof_event) cudaEventRecord(prof_event(), st);
             launches += 2;
         }
