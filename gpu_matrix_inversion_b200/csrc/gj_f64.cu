@@ -5,10 +5,11 @@
 //       .../matrix_inversion_no_pivots.cpp:10  (findCrr :41, fixRowKernel :60, copyCirColumn :50, fixColumnKernel :15)
 // (the entry points next to the FP32 hot path.)
 //
-// Round-1 form: the UNBLOCKED in-place schedule of gj_unblocked.cu in double precision -- three launches per column
-// (arg max, swap + normalise, rank-1 update), bit-identical to oracle/gj_oracle.c:gj_inplace_f64.  The rank-1 update
-// reads and writes the whole matrix once per column, so this path is HBM-bound (16 N^3 bytes): the roofline reported
-// for it is the copy bandwidth, not the FP64 pipe.  A blocked FP64 trailing update is the obvious next step.
+// Two schedules of the same arithmetic, both bit-identical to oracle/gj_oracle.c:gj_inplace_f64:
+//   * blocked (default, second half of this file): 64-column panels, explicit row interchanges, per panel one
+//     pivot-row recurrence and one trailing update -- 16 N^3 / 64 bytes of HBM traffic
+//   * unblocked (MATINV_FLAG_UNBLOCKED): the schedule of gj_unblocked.cu in double precision, three launches per column,
+//     the rank-1 update streams the whole matrix once per column (16 N^3 bytes, HBM-bound); kept as the cross-check
 //
 // The pivot candidate cannot ride in one 64-bit key as in FP32 (|x| alone is 63 bits), so partial results are
 // (magnitude bits, row, value) triples compared lexicographically: larger magnitude, then lower row.  The NaN rules are

@@ -111,7 +111,7 @@ int matinv_residual_f32_dev(const float *A_dev, const float *X_dev, int n, doubl
  *   matrix_inversion_FP64        (/root/reference/matrix_inv_solution/matrix_inversion_solution/matrix_inversion/matrix_inversion_FP64.cpp:13)
  *   matrix_inversion_no_pivots   (.../matrix_inversion_no_pivots.cpp:10)   -> flags |= MATINV_FLAG_NOPIVOT
  * Same conventions as the FP32 entries (row-major, 0 ok / 1 singular or non-finite / < 0 error, piv optional).
- * Round-1 implementation: unblocked in-place Gauss-Jordan, three launches per column, HBM-bound. */
+ * Blocked schedule with 64-column panels; MATINV_FLAG_UNBLOCKED selects the per-column schedule (cross-check). */
 int matinv_invert_f64(const double *A_host, int n, double *X_host, int *piv_host, int flags);
 int matinv_invert_f64_dev(const double *A_dev, int n, double *X_dev, int *piv_dev, void *stream, int flags);
 /* FP64-input twin of matinv_residual_f32_dev with a fourth output: out_host[4] = ||AX-I||_F^2, ||A||_F^2, ||X||_F^2,
