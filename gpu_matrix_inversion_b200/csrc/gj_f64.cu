@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(256) argmax_f64_kernel(const double *__restric
 }
 
 // (1') no pivoting: the candidate is the diagonal entry itself (findCrr, matrix_inversion_no_pivots.cpp:41)
-__global__ void diag_f64_kernel(const double *__restrict__ W, long long ld, int r, PivCand *__restrict__ part) {
+__global__ void diag_f64_kernel(const double *__restrict__ W, long long ld, int r, int col, PivCand *__restrict__ part) {
     PivCand c;
-    c.val = W[(long long)r * ld + r];
+    c.val = W[(long long)r * ld + col];
     c.mag = gj_mag64(c.val, true);
     c.row = r;
     c.pad = 0;
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(512) extract_f64_kernel(const double *__restri
 // to everything else.  Every element sees the FMA chain of the unblocked schedule, so the result is bit-identical
 // (tests compare the two paths and the oracle); HBM traffic drops from 16 N^3 to 16 N^3 / 64 bytes.
 #define F64_NB 64
+#define F64_RPC 32   // rows per CTA of the single-launch panel step (one arg-max partial per CTA)
 
 // (2b) pivot step t of a panel starting at column k0 (kw columns wide): reduce the partials, interchange rows r and p
 // on ALL columns, normalise the pivot row on the panel's columns only, record the multiplier column.
@@ -282,6 +283,96 @@ __global__ void __launch_bounds__(256) panel_rank1_f64_kernel(double *__restrict
     if (next_part) {   // uniform across the CTA
         block_best(mag, row, val, smag, srow, sval);
         if (threadIdx.x == 0 && threadIdx.y == 0) {
+            PivCand c;
+            c.mag = mag; c.val = val; c.row = row; c.pad = 0;
+            next_part[blockIdx.x] = c;
+        }
+    }
+}
+
+// (2c) pivot step t of a panel in ONE launch.  The panel's columns ping-pong between two buffers (`in` -> `out`; the first
+// step reads them from W, the last one writes them back), so no thread reads what another one writes and the pivot step
+// (2b) and the panel update (3b) need no kernel boundary between them.  Every CTA reduces the partials and forms the
+// normalised pivot row on the panel's columns itself; CTA 0 does the bookkeeping; the interchange of rows r and p on the
+// columns outside the panel is spread over all CTAs; one warp per row updates the panel's columns and the CTA leaves the
+// arg-max partial of the next column.
+__global__ void __launch_bounds__(256) panel_step_f64_kernel(const double *__restrict__ in, long long ld_in,
+                                                             double *__restrict__ out, long long ld_out,
+                                                             double *__restrict__ W, long long ld, int n, int r, int k0, int kw,
+                                                             int t, const PivCand *__restrict__ part, int nparts,
+                                                             PivCand *__restrict__ next_part, double *__restrict__ CT,
+                                                             double *__restrict__ pv, int *__restrict__ piv,
+                                                             int *__restrict__ info) {
+    __shared__ u64 smag[8];
+    __shared__ int srow[8];
+    __shared__ double sval[8];
+    __shared__ int sp;
+    __shared__ double sv;
+    const int lane = threadIdx.x, wy = threadIdx.y, lin = wy * 32 + lane;
+    u64 mag = 0;
+    int row = 0x7FFFFFFF;
+    double val = 0.0;
+    for (int g = lin; g < nparts; g += 256) {
+        const PivCand c = part[g];
+        if (cand_better(c.mag, c.row, mag, row)) { mag = c.mag; row = c.row; val = c.val; }
+    }
+    block_best(mag, row, val, smag, srow, sval);
+    if (lin == 0) { sp = row; sv = val; }
+    __syncthreads();
+    const int p = sp;
+    const double v = sv;
+    if (blockIdx.x == 0) {
+        if (lin == 0) {
+            piv[r] = p;
+            pv[t] = v;
+            if ((v == 0.0 || !isfinite(v)) && *info == 0) *info = r + 1;
+        }
+        if (lin < t && p != r) {   // multipliers of the panel's earlier steps follow their rows
+            const double a = CT[(long long)lin * ld + r], b = CT[(long long)lin * ld + p];
+            CT[(long long)lin * ld + r] = b;
+            CT[(long long)lin * ld + p] = a;
+        }
+    }
+    if (p != r) {   // rows r and p on the columns outside the panel
+        for (int c = blockIdx.x * 256 + lin; c < n; c += gridDim.x * 256) {
+            if (c >= k0 && c < k0 + kw) continue;
+            const double a = W[(long long)r * ld + c], b = W[(long long)p * ld + c];
+            W[(long long)r * ld + c] = b;
+            W[(long long)p * ld + c] = a;
+        }
+    }
+    // the panel's columns: F64_RPC rows per CTA, one warp per row at a time, two columns per lane
+    mag = 0; row = 0x7FFFFFFF; val = 0.0;
+    double u[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int jj = 2 * lane + q;
+        u[q] = (jj < kw) ? ((jj == t) ? 1.0 / v : in[(long long)p * ld_in + jj] / v) : 0.0;
+    }
+    for (int k = 0; k < F64_RPC / 8; k++) {
+        const int i = blockIdx.x * F64_RPC + wy + 8 * k;
+        if (i >= n) break;
+        const int src = (i == p) ? r : i;   // row p receives what row r held
+        const double c = (i == r) ? 0.0 : in[(long long)src * ld_in + t];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int jj = 2 * lane + q;
+            if (jj < kw) {
+                double a;
+                if (i == r) a = u[q];
+                else a = (jj == t) ? fma(-c, u[q], 0.0) : fma(-c, u[q], in[(long long)src * ld_in + jj]);
+                out[(long long)i * ld_out + jj] = a;
+                if (next_part && jj == t + 1 && i > r) {
+                    const u64 mq = gj_mag64(a, i == r + 1);
+                    if (cand_better(mq, i, mag, row)) { mag = mq; row = i; val = a; }
+                }
+            }
+        }
+        if (lane == 0) CT[(long long)t * ld + i] = c;
+    }
+    if (next_part) {
+        block_best(mag, row, val, smag, srow, sval);
+        if (lin == 0) {
             PivCand c;
             c.mag = mag; c.val = val; c.row = row; c.pad = 0;
             next_part[blockIdx.x] = c;
@@ -405,7 +496,7 @@ __global__ void __launch_bounds__(256, 2) trailing_f64_kernel(double *__restrict
 // ---------------------------------------------------------------------------------------------- host side
 void f64_workspace_free(F64Workspace &w) {
     cudaFree(w.W); cudaFree(w.urow); cudaFree(w.ccol); cudaFree(w.part); cudaFree(w.piv); cudaFree(w.colsrc); cudaFree(w.info);
-    cudaFree(w.io); cudaFree(w.CT); cudaFree(w.U); cudaFree(w.pv); cudaFree(w.upan);
+    cudaFree(w.io); cudaFree(w.CT); cudaFree(w.U); cudaFree(w.pv); cudaFree(w.upan); cudaFree(w.P[0]); cudaFree(w.P[1]);
     w = F64Workspace();
 }
 
@@ -417,7 +508,7 @@ cudaError_t f64_workspace_ensure(F64Workspace &w, int n, bool with_io) {
         if ((e = cudaMalloc(&w.W, sizeof(double) * ld * n)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.urow, sizeof(double) * ld)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.ccol, sizeof(double) * ld)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&w.part, sizeof(PivCand) * (size_t)((n + 7) / 8 + 1))) != cudaSuccess) return e;   // one per 8 rows (fused search)
+        if ((e = cudaMalloc(&w.part, sizeof(PivCand) * 2 * (size_t)((n + 7) / 8 + 1))) != cudaSuccess) return e;   // partials, double-buffered
         if ((e = cudaMalloc(&w.piv, sizeof(int) * (size_t)n)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.colsrc, sizeof(int) * (size_t)n)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.info, sizeof(int))) != cudaSuccess) return e;
@@ -425,6 +516,8 @@ cudaError_t f64_workspace_ensure(F64Workspace &w, int n, bool with_io) {
         if ((e = cudaMalloc(&w.U, sizeof(double) * ld * F64_NB)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.pv, sizeof(double) * F64_NB)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&w.upan, sizeof(double) * F64_NB)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.P[0], sizeof(double) * (size_t)n * F64_NB)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.P[1], sizeof(double) * (size_t)n * F64_NB)) != cudaSuccess) return e;
         w.n = n;
         w.ld = ld;
     }
@@ -454,18 +547,32 @@ int f64_invert_blocked_async(F64Workspace &w, const double *A_dev, int n, double
     const int ntile = (n + 63) / 64;
     for (int k0 = 0; k0 < n; k0 += F64_NB) {
         const int kw = (n - k0 < F64_NB) ? n - k0 : F64_NB;
-        const int nrow8 = (n + 7) / 8;
+        const int nrow8 = (n + 7) / 8, nstep = (n + F64_RPC - 1) / F64_RPC;
         for (int t = 0; t < kw; t++) {
             const int r = k0 + t;
-            // the search: fused into the previous step's panel update except for the first column of a panel
-            int np = nrow8;
-            if (nopivot) { diag_f64_kernel<<<1, 1, 0, st>>>(w.W, ld, r, w.part); np = 1; launches++; }
-            else if (t == 0) { argmax_f64_kernel<<<nparts, 256, 0, st>>>(w.W, ld, n, r, r, w.part); np = nparts; launches++; }
-            panel_pivot_f64_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.W, ld, n, r, k0, kw, t, w.part, np, w.CT, w.upan, w.pv,
-                                                                    w.piv, w.info);
+            if (kw == 1) {   // a one-column panel cannot ping-pong (it would read and write W): the two in-place kernels
+                if (nopivot) diag_f64_kernel<<<1, 1, 0, st>>>(w.W, ld, r, r, w.part);
+                else argmax_f64_kernel<<<nparts, 256, 0, st>>>(w.W, ld, n, r, r, w.part);
+                panel_pivot_f64_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.W, ld, n, r, k0, kw, t, w.part, nopivot ? 1 : nparts, w.CT,
+                                                                        w.upan, w.pv, w.piv, w.info);
+                panel_rank1_f64_kernel<<<nrow8, dim3(32, 8), 0, st>>>(w.W, ld, n, r, k0, kw, t, w.CT, w.upan, nullptr);
+                launches += 3;
+                continue;
+            }
+            const double *in = (t == 0) ? w.W + k0 : w.P[(t - 1) & 1];
+            const long long ld_in = (t == 0) ? ld : F64_NB;
+            double *out = (t == kw - 1) ? w.W + k0 : w.P[t & 1];
+            const long long ld_out = (t == kw - 1) ? ld : F64_NB;
+            // the search: left behind by the previous step except for the first column of a panel (and without pivoting).
+            // The partials are read at the top of the kernel and rewritten at its end: two buffers, alternating.
+            PivCand *pin = w.part + (size_t)(t & 1) * (nstep + 1), *pout = w.part + (size_t)((t + 1) & 1) * (nstep + 1);
+            int np = nstep;
+            if (nopivot) { diag_f64_kernel<<<1, 1, 0, st>>>(in, ld_in, r, t, pin); np = 1; launches++; }
+            else if (t == 0) { argmax_f64_kernel<<<nparts, 256, 0, st>>>(w.W, ld, n, r, r, pin); np = nparts; launches++; }
             const bool fuse = !nopivot && t + 1 < kw;
-            panel_rank1_f64_kernel<<<nrow8, dim3(32, 8), 0, st>>>(w.W, ld, n, r, k0, kw, t, w.CT, w.upan, fuse ? w.part : nullptr);
-            launches += 2;
+            panel_step_f64_kernel<<<nstep, dim3(32, 8), 0, st>>>(in, ld_in, out, ld_out, w.W, ld, n, r, k0, kw, t, pin, np,
+                                                                 fuse ? pout : nullptr, w.CT, w.pv, w.piv, w.info);
+            launches++;
         }
         if (n > kw) {
             rowblock_f64_kernel<<<(n + 127) / 128, 128, sizeof(F64RowblockSmem), st>>>(w.W, ld, n, k0, kw, w.CT, w.pv, w.U);
@@ -498,7 +605,7 @@ int f64_invert_async(F64Workspace &w, const double *A_dev, int n, double *X_dev,
     launches++;
     const int nparts = (n + 255) / 256;
     for (int r = 0; r < n; r++) {
-        if (nopivot) diag_f64_kernel<<<1, 1, 0, st>>>(w.W, ld, r, w.part);
+        if (nopivot) diag_f64_kernel<<<1, 1, 0, st>>>(w.W, ld, r, r, w.part);
         else argmax_f64_kernel<<<nparts, 256, 0, st>>>(w.W, ld, n, r, r, w.part);
         swap_normalize_f64_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.W, ld, n, r, w.part, nopivot ? 1 : nparts, w.urow, w.ccol,
                                                                    w.piv, w.info);

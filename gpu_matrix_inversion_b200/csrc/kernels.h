@@ -86,6 +86,7 @@ struct PivCand;
 struct F64Workspace {
     double *W = nullptr, *urow = nullptr, *ccol = nullptr, *io = nullptr;
     double *CT = nullptr, *U = nullptr, *pv = nullptr, *upan = nullptr;   // blocked schedule: multipliers (transposed), snapshots
+    double *P[2] = {nullptr, nullptr};                                     // panel ping-pong (n x 64 each)
     PivCand *part = nullptr;
     int *piv = nullptr, *colsrc = nullptr, *info = nullptr;
     int n = 0;
