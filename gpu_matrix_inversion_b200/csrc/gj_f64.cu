@@ -418,6 +418,11 @@ __global__ void __launch_bounds__(128) rowblock_f64_kernel(double *__restrict__ 
 // (5) trailing update: 128 x 64 tiles, 256 threads x (8 x 4) doubles; the tile column of the panel is skipped (k0 is a
 // multiple of 64), the pivot rows are computed along and not stored.  Accumulators are seeded from W and take the kw
 // FMAs in step order.  The whole K extent (kw <= 64) of both operands sits in shared memory: 96 KB, two CTAs per SM.
+__device__ __forceinline__ void f64_cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 struct F64GemmSmem {
     double a[F64_NB][128];   // a[t][ii] = CT[t][i0 + ii]
     double b[F64_NB][64];    // b[t][jj] = U[t][j0 + jj]
@@ -432,16 +437,30 @@ __global__ void __launch_bounds__(256, 2) trailing_f64_kernel(double *__restrict
     tj += (tj >= skip);
     const int i0 = blockIdx.y * 128, j0 = tj * 64;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    for (int e = tid; e < kw * 128; e += 256) {
-        const int t = e >> 7, c = e & 127;
-        s.a[t][c] = (i0 + c < n) ? CT[(long long)t * ld + i0 + c] : 0.0;
-    }
-    for (int e = tid; e < kw * 64; e += 256) {
-        const int t = e >> 6, c = e & 63;
-        s.b[t][c] = (j0 + c < n) ? U[(long long)t * ld + j0 + c] : 0.0;
+    const bool full = (i0 + 128 <= n) && (j0 + 64 <= n);
+    if (full) {
+        // both operands with 16-byte cp.async: every copy is in flight at once (a guarded load/store loop pays one
+        // global-memory latency per iteration)
+        for (int e = tid; e < kw * 64; e += 256) {
+            const int t = e >> 6, c = (e & 63) * 2;
+            f64_cp_async16(&s.a[t][c], CT + (long long)t * ld + i0 + c);
+        }
+        for (int e = tid; e < kw * 32; e += 256) {
+            const int t = e >> 5, c = (e & 31) * 2;
+            f64_cp_async16(&s.b[t][c], U + (long long)t * ld + j0 + c);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+        for (int e = tid; e < kw * 128; e += 256) {
+            const int t = e >> 7, c = e & 127;
+            s.a[t][c] = (i0 + c < n) ? CT[(long long)t * ld + i0 + c] : 0.0;
+        }
+        for (int e = tid; e < kw * 64; e += 256) {
+            const int t = e >> 6, c = e & 63;
+            s.b[t][c] = (j0 + c < n) ? U[(long long)t * ld + j0 + c] : 0.0;
+        }
     }
     double acc[8][4];
-    const bool full = (i0 + 128 <= n) && (j0 + 64 <= n);
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         const int i = i0 + ty * 8 + q;
@@ -457,6 +476,7 @@ __global__ void __launch_bounds__(256, 2) trailing_f64_kernel(double *__restrict
             }
         }
     }
+    if (full) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 #pragma unroll 4
     for (int t = 0; t < kw; t++) {
