@@ -561,7 +561,8 @@ cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long l
     }
     if (n <= 16384) {
         // Two shapes for the same 16 x n sub-panel.  512 threads x 2 rows is the faster kernel (25 vs 31 us) and is used
-        // while the panel is on the critical path; from n = 12288 the panel is hidden behind the trailing update and what
+        // while the panel is on the critical path (measured better up to n = 12288: 80.6 vs 88.9 ms); near n = 16384 the panel
+        // is hidden behind the trailing update and what
         // counts is what its CTAs displace: 256 threads x 4 rows stay within 128 registers, so a CTA fits beside one CTA of
         // the trailing update instead of taking the whole SM (N=16384: 171.8 -> 169.0 ms).  MATINV_K1_THREADS overrides.
         static int forced = -1;
@@ -569,7 +570,7 @@ cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long l
             const char *e = getenv("MATINV_K1_THREADS");
             forced = e ? atoi(e) : 0;
         }
-        const int th = forced ? forced : (n >= 12288 ? 256 : 512);
+        const int th = forced ? forced : (n >= 15360 ? 256 : 512);
         if (th == 256) return launch_subpanel_t<16, 4, 256>(16, SP_ARGS);
         return launch_subpanel_t<16, 2, 512>(16, SP_ARGS);
     }
@@ -591,8 +592,8 @@ static void launch_panel_update_t(const float *in, long long ld_in, float *out, 
                                                                         pv, ps, kb);
 }
 
-// Rows per CTA: 64 while that is a single wave of CTAs (the kernel is then on the critical path of a panel-bound
-// inversion: 12.3 ms against 14.2 ms at n = 4096), 256 above (it runs beside the trailing update and the time its CTAs
+// Rows per CTA: 64 while the panel is on the critical path (12.3 ms against 14.2 ms at n = 4096, 57.3 against 58.1 at
+// n = 10240), 256 above (80.6 against 81.5 ms at n = 12288) (it runs beside the trailing update and the time its CTAs
 // hold SM slots is what counts: 171.7 ms against 178.5 ms at n = 16384).  MATINV_UPDATE_ROWS = 64 | 128 | 256 | 512 overrides.
 void launch_panel_update(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0, int sw,
                          int wfull, float *CmT, long long ldc, const int *piv, const float *pv, PanelState *ps, int kb,
@@ -602,7 +603,7 @@ void launch_panel_update(const float *in, long long ld_in, float *out, long long
         const char *e = getenv("MATINV_UPDATE_ROWS");
         forced = e ? atoi(e) : 0;
     }
-    const int rows = forced ? forced : (n <= 64 * 148 ? 64 : 256);
+    const int rows = forced ? forced : (n <= 11264 ? 64 : 256);
     if (rows == 64) launch_panel_update_t<64>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
     else if (rows == 128) launch_panel_update_t<128>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
     else if (rows == 512) launch_panel_update_t<512>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
