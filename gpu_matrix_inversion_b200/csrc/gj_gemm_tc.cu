@@ -1,0 +1,290 @@
+// Optional trailing update on the 5th-generation tensor cores: 3xTF32 with tcgen05.mma and a TMEM accumulator
+// (north_star kernel (3), "optional 3xTF32 tcgen05/TMEM variant gated by residual"; MATINV_FLAG_TF32X3).
+//
+// Same contraction as gj_gemm.cu -- the reference's fixColumnKernel
+// (/root/reference/Matlab/mat_inv_32/mat_inv_32/mat_inv_32.cpp:13-57) applied 128 times,
+//
+//     W[i][j] <- W[i][j] - sum_t C[i][t] * U[t][j]        (i outside the pivot rows, j outside the panel)
+//
+// but NOT the reference's FMA chain: every FP32 operand is split into two TF32 numbers, x = hi + lo
+// (hi = rna_tf32(x), lo = rna_tf32(x - hi); 11 + 11 significant bits), and the product is evaluated as
+// lo*hi + hi*lo + hi*hi on the tensor cores with an FP32 accumulator that starts from zero.  The dropped lo*lo term and
+// the tensor core's accumulation order make the result differ from the FP32 SIMT kernel in the last 2-3 bits, so this
+// path can change pivot choices downstream.  It is therefore never the parity path: the shim accepts its result only
+// if the residual estimate passes (matinv_shim.cu: tf32x3 gate) and reruns the FP32 SIMT schedule otherwise.
+//
+// Two launches per trailing update:
+//   tf32_split_kernel       reads the K-major operands CmT[t][i] / U[t][j] once and writes, per 128-row tile, the
+//                           hi and lo parts in the exact shared-memory image tcgen05.mma wants (K-major, no swizzle:
+//                           8x16-byte core matrices, 128 contiguous bytes each), so that the GEMM kernel can stage
+//                           an operand with ONE linear bulk copy and needs no tensor map.  64 MiB at N=16384, L2-resident.
+//   trailing_tf32x3_kernel  one 128x128 tile of W per CTA, 192 threads, 2 CTAs per SM:
+//                             warp 0   allocates 128 TMEM columns; lane 0 issues the MMAs (6 per 16-deep K stage)
+//                             warp 1   lane 0 = producer: cp.async.bulk (TMA, linear) into a 3-stage 32 KiB ring,
+//                                      completion on mbarriers; slots are released by tcgen05.commit
+//                             warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns), W - D, store
+//
+// What bounds it: 2 * 64 KiB of W traffic per tile against 3 * 2*128^3 tensor flops -- at the measured 6.4 TB/s the
+// W traffic of one trailing update at N=16384 (2.1 GB) takes 0.33 ms, the 3xTF32 MMAs 0.18 ms at the nominal TF32 peak:
+// HBM-bound, where the FP32 SIMT kernel is FP32-pipe-bound at 1.2 ms.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int TC_TILE = 128;                           // tile edge == panel width == MMA M == MMA N
+constexpr int TC_BK = 16;                              // K per pipeline stage (2 MMA k-steps of 8)
+constexpr int TC_KCH = 128 / TC_BK;                    // stages per tile
+constexpr int TC_STAGES = 3;                           // ring depth
+constexpr int TC_CHUNK_FLOATS = TC_TILE * TC_BK;       // one operand part (hi or lo) of one stage: 2048 floats
+constexpr int TC_CHUNK_BYTES = TC_CHUNK_FLOATS * 4;    // 8 KiB
+constexpr int TC_STAGE_BYTES = 4 * TC_CHUNK_BYTES;     // A_hi | A_lo | B_hi | B_lo = 32 KiB
+constexpr int TC_TILE_IMG_FLOATS = TC_KCH * 2 * TC_CHUNK_FLOATS;  // image of one 128-row tile, all K: 128 KiB
+constexpr int TC_TMEM_COLS = 128;                      // 128 x 128 FP32 accumulator
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;  // + slack to align the ring to 1 KiB
+
+// Inside one 8 KiB chunk (128 rows x 16 k, K-major, no swizzle): core matrix = 8 rows x 16 bytes (4 TF32), stored as 128
+// contiguous bytes; the 16 row groups of one 4-wide K slice follow each other (SBO = 128 B), the 4 K slices are 2 KiB
+// apart (LBO = 2048 B).  Element (r, k) sits at float offset (k/4)*512 + (r/8)*32 + (r%8)*4 + (k%4).
+constexpr unsigned TC_LBO = 2048, TC_SBO = 128;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// split + re-tile: S is K-major (S[k][c], leading dimension lds); tile t covers columns t*128 .. t*128+127.
+// Rows k >= kb are written as zeros (a narrower last panel contributes nothing).
+__global__ void __launch_bounds__(256)
+tf32_split_kernel(const float *__restrict__ SA, long long ldsa, float *__restrict__ imgA, int tilesA,
+                  const float *__restrict__ SB, long long ldsb, float *__restrict__ imgB, int kb) {
+    int t = blockIdx.x;
+    const float *S = SA;
+    long long lds = ldsa;
+    float *img = imgA;
+    if (t >= tilesA) { t -= tilesA; S = SB; lds = ldsb; img = imgB; }
+    const int r = threadIdx.x & 127;
+    const float *src = S + (long long)t * TC_TILE + r;
+    float *dst = img + (long long)t * TC_TILE_IMG_FLOATS;
+#pragma unroll 4
+    for (int k4 = threadIdx.x >> 7; k4 < 32; k4 += 2) {
+        const int k = 4 * k4;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float x = (k + e < kb) ? src[(long long)(k + e) * lds] : 0.0f;
+            hi[e] = to_tf32(x);
+            lo[e] = to_tf32(x - hi[e]);
+        }
+        const int off = ((k >> 4) * 2) * TC_CHUNK_FLOATS + ((k & 15) >> 2) * 512 + (r >> 3) * 32 + (r & 7) * 4;
+        *reinterpret_cast<float4 *>(dst + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4 *>(dst + off + TC_CHUNK_FLOATS) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier / TMA / tcgen05 wrappers (inline PTX, sm_100a)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must fail loudly (trap -> CUDA error -> MATINV_E_CUDA), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = smem_u32(bar);
+    const long long t0 = clock64();
+    for (unsigned spins = 0;; spins++) {
+        unsigned ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spins & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();  // ~2 s
+    }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], M = N = 128, K = 8, TF32 inputs, FP32 accumulator
+__device__ __forceinline__ void tc_mma_tf32(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b, unsigned idesc,
+                                            unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Shared-memory matrix descriptor (K-major, SWIZZLE_NONE): start address, leading (K) and stride (8-row group) byte
+// offsets, all >> 4; bits 46-47 = 1 (sm_100 descriptor version).
+__device__ __forceinline__ unsigned long long tc_desc(unsigned smem_addr) {
+    return (unsigned long long)((smem_addr & 0x3FFFFu) >> 4) | ((unsigned long long)(TC_LBO >> 4) << 16) |
+           ((unsigned long long)(TC_SBO >> 4) << 32) | (1ull << 46);
+}
+// Instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major (bits 15, 16 = 0),
+// N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr unsigned TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_TILE >> 3) << 17) | ((unsigned)(TC_TILE >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&d)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]),
+          "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]),
+          "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]),
+          "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 2)
+trailing_tf32x3_kernel(float *__restrict__ W, long long ld, int row_skip, int col_skip, int col_skip_n,
+                       const float *__restrict__ imgA, const float *__restrict__ imgB) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_done;
+    __shared__ unsigned tmem_slot;
+
+    int tj = blockIdx.x, ti = blockIdx.y;
+    if (col_skip >= 0 && tj >= col_skip) tj += col_skip_n;  // the panel's tile column(s)
+    ti += (ti >= row_skip);                                 // the pivot rows' tile row
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned ring = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TC_STAGES; s++) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(&bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // whole warp: TMEM allocation, base address lands in shared memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"((unsigned)TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *reinterpret_cast<volatile unsigned *>(&tmem_slot);
+
+    if (warp == 1) {
+        // ===== producer: two 16 KiB linear bulk copies per stage (A hi|lo, B hi|lo)
+        if (lane == 0) {
+            const float *ga = imgA + (long long)ti * TC_TILE_IMG_FLOATS;
+            const float *gb = imgB + (long long)tj * TC_TILE_IMG_FLOATS;
+            for (int kc = 0; kc < TC_KCH; kc++) {
+                const int s = kc % TC_STAGES;
+                if (kc >= TC_STAGES) mbar_wait(&bar_empty[s], (unsigned)((kc / TC_STAGES) - 1) & 1u);
+                mbar_expect_tx(&bar_full[s], TC_STAGE_BYTES);
+                const unsigned dst = ring + (unsigned)s * TC_STAGE_BYTES;
+                bulk_g2s(dst, ga + (long long)kc * 2 * TC_CHUNK_FLOATS, 2 * TC_CHUNK_BYTES, &bar_full[s]);
+                bulk_g2s(dst + 2 * TC_CHUNK_BYTES, gb + (long long)kc * 2 * TC_CHUNK_FLOATS, 2 * TC_CHUNK_BYTES, &bar_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 0) {
+        // ===== MMA issuer: per 8-deep k-step  D += A_lo*B_hi ; D += A_hi*B_lo ; D += A_hi*B_hi
+        if (lane == 0) {
+            for (int kc = 0; kc < TC_KCH; kc++) {
+                const int s = kc % TC_STAGES;
+                mbar_wait(&bar_full[s], (unsigned)(kc / TC_STAGES) & 1u);
+                tc_fence_after();
+                const unsigned base = ring + (unsigned)s * TC_STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ks++) {
+                    const unsigned o = (unsigned)ks * 2u * TC_LBO;  // 8 k = two 4-wide K slices
+                    const unsigned long long a_hi = tc_desc(base + o), a_lo = tc_desc(base + TC_CHUNK_BYTES + o);
+                    const unsigned long long b_hi = tc_desc(base + 2 * TC_CHUNK_BYTES + o), b_lo = tc_desc(base + 3 * TC_CHUNK_BYTES + o);
+                    tc_mma_tf32(tmem, a_lo, b_hi, TC_IDESC, (kc | ks) != 0);
+                    tc_mma_tf32(tmem, a_hi, b_lo, TC_IDESC, 1u);
+                    tc_mma_tf32(tmem, a_hi, b_hi, TC_IDESC, 1u);
+                }
+                tc_commit(&bar_empty[s]);  // slot free once these MMAs have read it
+            }
+            tc_commit(&bar_done);          // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; lane l owns row 32*(w%4) + l of the tile
+        const int q = warp & 3;
+        float *row = W + ((long long)ti * TC_TILE + q * 32 + lane) * ld + (long long)tj * TC_TILE;
+        const unsigned taddr = tmem + ((unsigned)(q * 32) << 16);
+        float4 c[8], cn[8];
+#pragma unroll
+        for (int v = 0; v < 8; v++) c[v] = *reinterpret_cast<const float4 *>(row + 4 * v);  // in flight during the MMAs
+        mbar_wait(&bar_done, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < TC_TILE; c0 += 32) {
+            unsigned d[32];
+            tmem_ld32(taddr + (unsigned)c0, d);
+            if (c0 + 32 < TC_TILE) {
+#pragma unroll
+                for (int v = 0; v < 8; v++) cn[v] = *reinterpret_cast<const float4 *>(row + c0 + 32 + 4 * v);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+                float4 o;
+                o.x = c[v].x - __uint_as_float(d[4 * v + 0]);
+                o.y = c[v].y - __uint_as_float(d[4 * v + 1]);
+                o.z = c[v].z - __uint_as_float(d[4 * v + 2]);
+                o.w = c[v].w - __uint_as_float(d[4 * v + 3]);
+                *reinterpret_cast<float4 *>(row + c0 + 4 * v) = o;
+            }
+#pragma unroll
+            for (int v = 0; v < 8; v++) c[v] = cn[v];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)TC_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace
+
+size_t tf32x3_image_bytes(int tiles) { return (size_t)tiles * TC_TILE_IMG_FLOATS * sizeof(float); }
+
+// Same tile selection as launch_trailing_gemm_ex (gj_gemm.cu).  imgA must hold nrow_tiles tile images, imgB ncol_tiles; both are
+// scratch owned by the caller and must not be shared with a launch that may run concurrently on another stream.
+cudaError_t launch_trailing_tf32x3(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n,
+                                   int kb, const float *CmT, long long ldc, const float *U, long long ldu, float *imgA, float *imgB,
+                                   cudaStream_t st) {
+    static bool configured[64] = {};
+    if (first_use_on_device(configured)) {
+        cudaError_t e = cudaFuncSetAttribute(trailing_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+    }
+    const int gx = ncol_tiles - (col_skip >= 0 ? col_skip_n : 0), gy = nrow_tiles - 1;
+    if (gx <= 0 || gy <= 0) return cudaSuccess;
+    tf32_split_kernel<<<nrow_tiles + ncol_tiles, 256, 0, st>>>(CmT, ldc, imgA, nrow_tiles, U, ldu, imgB, kb);
+    trailing_tf32x3_kernel<<<dim3(gx, gy), 192, TC_SMEM_BYTES, st>>>(W, ld, row_skip, col_skip, col_skip_n, imgA, imgB);
+    return cudaGetLastError();
+}

@@ -63,6 +63,16 @@ void launch_trailing_gemm(float *W, long long ld, int npad, int k0, int kb, cons
 void launch_trailing_gemm_ex(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n, int kb,
                              const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st);
 
+// ---- gj_gemm_tc.cu : the same trailing update as 3xTF32 on tcgen05 tensor cores (TMEM accumulator); NOT bit-identical
+size_t tf32x3_image_bytes(int tiles);
+cudaError_t launch_trailing_tf32x3(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n,
+                                   int kb, const float *CmT, long long ldc, const float *U, long long ldu, float *imgA, float *imgB,
+                                   cudaStream_t st);
+
+// ---- gj_probe.cu : O(N^2) randomised estimate of ||A X - I||_F (gate of the 3xTF32 path)
+size_t probe_scratch_bytes(int n);
+cudaError_t run_probe_residual(const float *A, const float *X, int n, double *scratch, double *out_host, cudaStream_t st);
+
 // ---- gj_finish.cu : deferred column permutation + extraction + isfinite scan
 void launch_colperm_build(const int *piv, int n, int *colsrc, cudaStream_t st);
 void launch_extract(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check,

@@ -76,6 +76,11 @@ struct Workspace {
     // second set for the look-ahead schedule: panel k+1 is factored while the trailing update of panel k runs
     float *CmT2 = nullptr, *pv2 = nullptr;
     PanelState *ps2 = nullptr;
+    // 3xTF32 path (gj_gemm_tc.cu): pre-tiled hi/lo operand images, one set per stream (main / panel stream) because the two
+    // streams run their trailing updates concurrently; probe scratch of the residual gate
+    float *tcA[2] = {nullptr, nullptr}, *tcB[2] = {nullptr, nullptr};
+    double *probe = nullptr;
+    int tc_npad = 0;
 };
 
 struct Context {
@@ -88,6 +93,8 @@ struct Context {
     cudaStream_t stream = nullptr;
     float *hostio = nullptr;  // device staging for the host-pointer entries
     size_t hostio_bytes = 0;
+    float *hostx = nullptr;   // second staging buffer: the gated 3xTF32 host entry keeps A intact while X is written
+    size_t hostx_bytes = 0;
     int *hostio_i = nullptr;
     size_t hostio_i_bytes = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -126,6 +133,7 @@ void free_ws(Workspace &w) {
     cudaFree(w.urow); cudaFree(w.ccol); cudaFree(w.pv); cudaFree(w.part[0]); cudaFree(w.part[1]);
     cudaFree(w.piv); cudaFree(w.colsrc); cudaFree(w.info); cudaFree(w.ps);
     cudaFree(w.CmT2); cudaFree(w.pv2); cudaFree(w.ps2);
+    cudaFree(w.tcA[0]); cudaFree(w.tcA[1]); cudaFree(w.tcB[0]); cudaFree(w.tcB[1]); cudaFree(w.probe);
     w = Workspace();
 }
 
@@ -134,6 +142,7 @@ void release_locked() {
     f64_workspace_free(g.wsd);
     cudaFree(g.hostio); g.hostio = nullptr; g.hostio_bytes = 0;
     cudaFree(g.hostio_i); g.hostio_i = nullptr; g.hostio_i_bytes = 0;
+    cudaFree(g.hostx); g.hostx = nullptr; g.hostx_bytes = 0;
     if (g.copy_stream) {
         cudaEventDestroy(g.ev_chunk[0]); cudaEventDestroy(g.ev_chunk[1]);
         cudaStreamDestroy(g.copy_stream);
@@ -249,6 +258,47 @@ bool use_panel_v1(int n) {
     return mode == 1 && subpanel_supported(n);
 }
 
+// ---- 3xTF32 tensor-core trailing update (MATINV_FLAG_TF32X3) -------------------------------------------------------
+// g_tc.on is set by factor_locked (under the context lock) for the duration of one factorisation; the schedules call
+// trailing_ex() wherever they used to call the FP32 SIMT launcher, `side` = 1 for launches on the panel stream.
+struct TcState {
+    bool on = false;
+    bool used = false;            // the last factorisation ran its trailing updates on the tensor cores
+    double last_estimate = -1.0;  // residual estimate of the last gated inversion
+    int last_fallback = 0;        // 1 = the gate rejected the 3xTF32 result and the FP32 SIMT schedule was run
+    long long inversions = 0, fallbacks = 0;
+} g_tc;
+
+int ensure_tc(Workspace &w) {
+    if (w.tc_npad == w.npad) return 0;
+    for (int s = 0; s < 2; s++) {
+        cudaFree(w.tcA[s]); cudaFree(w.tcB[s]);
+        w.tcA[s] = w.tcB[s] = nullptr;
+    }
+    cudaFree(w.probe);
+    w.probe = nullptr;
+    w.tc_npad = 0;
+    const int nt = w.npad / MATINV_NB;
+    for (int s = 0; s < 2; s++) {
+        CK(cudaMalloc(&w.tcA[s], tf32x3_image_bytes(nt)));
+        CK(cudaMalloc(&w.tcB[s], tf32x3_image_bytes(s == 0 ? nt : 1)));  // the panel stream only ever updates one tile column
+    }
+    CK(cudaMalloc(&w.probe, probe_scratch_bytes(w.npad)));
+    w.tc_npad = w.npad;
+    return 0;
+}
+
+void trailing_ex(Workspace &w, float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n,
+                 int kb, const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st, int side) {
+    if (g_tc.on && (side == 0 || ncol_tiles == 1)) {
+        launch_trailing_tf32x3(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, w.tcA[side],
+                               w.tcB[side], st);
+        COUNT_LAUNCH(1);  // the split kernel; callers count the update itself
+        return;
+    }
+    launch_trailing_gemm_ex(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, st);
+}
+
 // Blocked right-looking: per 128-wide panel  factor -> (swaps + recurrence) -> trailing GEMM.
 void schedule_blocked(Workspace &w, int n, cudaStream_t st) {
     const long long ld = w.npad;
@@ -260,7 +310,7 @@ void schedule_blocked(Workspace &w, int n, cudaStream_t st) {
         if (w.npad > MATINV_NB) {
             launch_rowblock(w.W, ld, w.npad, k0, kb, w.CmT, ld, w.pv, w.ps, w.U, ld, st);
             if (g_prof.on) cudaEventRecord(prof_event(), st);
-            launch_trailing_gemm(w.W, ld, w.npad, k0, kb, w.CmT, ld, w.U, ld, st);
+            trailing_ex(w, w.W, ld, w.npad / MATINV_NB, w.npad / MATINV_NB, k0 / MATINV_NB, k0 / MATINV_NB, 1, kb, w.CmT, ld, w.U, ld, st, 0);
             if (g_prof.on) {
                 cudaEventRecord(prof_event(), st);
                 const double m = (double)(w.npad - MATINV_NB);
@@ -319,13 +369,13 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
             cudaEventRecord(g.ev_a, st);   // everything up to GEMM_B(k-1) (and panel k, joined below / before the loop)
             cudaStreamWaitEvent(sp, g.ev_a, 0);
             launch_rowblock_ex(w.W + k1, ld, MATINV_NB, k0, kb, 0, 0, CmT[b], ld, pv[b], ps[b], w.U + k1, ld, sp);
-            launch_trailing_gemm_ex(w.W + k1, ld, nt, 1, k, -1, 0, kb, CmT[b], ld, w.U + k1, ld, sp);
+            trailing_ex(w, w.W + k1, ld, nt, 1, k, -1, 0, kb, CmT[b], ld, w.U + k1, ld, sp, 1);
             COUNT_LAUNCH(launch_panel_factor(w.W + k1, ld, n, k1, kb1, CmT[b ^ 1], ld, w.piv, pv[b ^ 1], w.info, ps[b ^ 1], w.P[0],
                                              w.P[1], sp));
             cudaEventRecord(g.ev_p, sp);
             launch_rowblock_ex(w.W, ld, w.npad, k0, kb, k, 2, CmT[b], ld, pv[b], ps[b], w.U, ld, st);
             if (g_prof.on) cudaEventRecord(prof_event(), st);
-            launch_trailing_gemm_ex(w.W, ld, nt, nt, k, k, 2, kb, CmT[b], ld, w.U, ld, st);
+            trailing_ex(w, w.W, ld, nt, nt, k, k, 2, kb, CmT[b], ld, w.U, ld, st, 0);
             if (g_prof.on) {
                 cudaEventRecord(prof_event(), st);
                 const double m = (double)(w.npad - MATINV_NB);
@@ -342,18 +392,18 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
             const int k1 = k0 + MATINV_NB;
             const int kb1 = (n - k1 < MATINV_NB) ? n - k1 : MATINV_NB;
             // GEMM_A: tile column k+1 only
-            launch_trailing_gemm_ex(w.W + k1, ld, nt, 1, k, -1, 0, kb, CmT[b], ld, w.U + k1, ld, st);
+            trailing_ex(w, w.W + k1, ld, nt, 1, k, -1, 0, kb, CmT[b], ld, w.U + k1, ld, st, 1);
             cudaEventRecord(g.ev_a, st);
             cudaStreamWaitEvent(sp, g.ev_a, 0);
             COUNT_LAUNCH(launch_panel_factor(w.W + k1, ld, n, k1, kb1, CmT[b ^ 1], ld, w.piv, pv[b ^ 1], w.info, ps[b ^ 1], w.P[0],
                                              w.P[1], sp));
             cudaEventRecord(g.ev_p, sp);
             // GEMM_B: every other tile column (skips k and k+1)
-            launch_trailing_gemm_ex(w.W, ld, nt, nt, k, k, 2, kb, CmT[b], ld, w.U, ld, st);
+            trailing_ex(w, w.W, ld, nt, nt, k, k, 2, kb, CmT[b], ld, w.U, ld, st, 0);
             cudaStreamWaitEvent(st, g.ev_p, 0);
             COUNT_LAUNCH(2);
         } else {
-            launch_trailing_gemm_ex(w.W, ld, nt, nt, k, k, 1, kb, CmT[b], ld, w.U, ld, st);
+            trailing_ex(w, w.W, ld, nt, nt, k, k, 1, kb, CmT[b], ld, w.U, ld, st, 0);
             COUNT_LAUNCH(1);
         }
         if (g_prof.on) {
@@ -370,19 +420,25 @@ bool use_lookahead(int n, int npad) {
 
 // load + factorisation + column gather list; leaves M = inv(P A) in the workspace
 int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags) {
-    if (flags & MATINV_FLAG_TF32X3) return fail(MATINV_E_UNSUPPORTED, "3xTF32 trailing update is not built in this round");
     const int npad = ((n + MATINV_NB - 1) / MATINV_NB) * MATINV_NB;
     int rc = ensure_ws(npad);
     if (rc) return rc;
     Workspace &w = g.ws;
+    g_tc.on = g_tc.used = false;
+    if ((flags & MATINV_FLAG_TF32X3) && !(flags & MATINV_FLAG_UNBLOCKED) && npad > MATINV_NB) {
+        rc = ensure_tc(w);
+        if (rc) return rc;
+        g_tc.on = g_tc.used = true;
+    }
     CK(cudaMemsetAsync(w.info, 0, sizeof(int), st));
     launch_load(A_dev, n, w.W, npad, npad, st);
     if (flags & MATINV_FLAG_UNBLOCKED) schedule_unblocked(w, n, st);
     else if (use_lookahead(n, npad)) {
         rc = ensure_lookahead();
-        if (rc) return rc;
+        if (rc) { g_tc.on = false; return rc; }
         schedule_lookahead(w, n, st);
     } else schedule_blocked(w, n, st);
+    g_tc.on = false;
     COUNT_LAUNCH(3);
     launch_colperm_build(w.piv, n, w.colsrc, st);
     CK(cudaGetLastError());
@@ -401,7 +457,7 @@ int status_locked(cudaStream_t st) {
     return MATINV_OK;
 }
 
-int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cudaStream_t st, int flags) {
+int invert_dev_once(const float *A_dev, int n, float *X_dev, int *piv_dev, cudaStream_t st, int flags) {
     int rc = factor_locked(A_dev, n, st, flags);
     if (rc) return rc;
     Workspace &w = g.ws;
@@ -409,6 +465,35 @@ int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cud
     if (piv_dev) CK(cudaMemcpyAsync(piv_dev, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
     return status_locked(st);
+}
+
+// The 3xTF32 result is accepted only if the residual estimate ||A X - I||_F / (n ||A||_F ||X||_F) (gj_probe.cu) passes
+// north_star's 1e-5 bound; otherwise -- and whenever the tensor-core run reports a singular matrix, because that
+// verdict has to be the FP32 algorithm's -- the FP32 SIMT schedule is run on the same input.  Both paths are CUDA.
+int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cudaStream_t st, int flags) {
+    if (flags & MATINV_FLAG_TF32X3) {
+        if (A_dev == X_dev)
+            return fail(MATINV_E_INVALID, "MATINV_FLAG_TF32X3: A and X must not alias (the residual gate reads A after X is written)");
+        int rc = invert_dev_once(A_dev, n, X_dev, piv_dev, st, flags);
+        if (rc < 0) return rc;
+        if (!g_tc.used) return rc;  // n <= 128 or unblocked: no trailing update ran, the result is the FP32 one already
+        g_tc.inversions++;
+        g_tc.last_fallback = 0;
+        g_tc.last_estimate = -1.0;
+        if (rc == MATINV_OK) {
+            if (flags & MATINV_FLAG_NOCHECK) return rc;  // caller opted out of every check (timing runs)
+            double r[3] = {0, 0, 0};
+            CK(run_probe_residual(A_dev, X_dev, n, g.ws.probe, r, st));
+            COUNT_LAUNCH(2);
+            const double est = sqrt(r[0]) / ((double)n * sqrt(r[1]) * sqrt(r[2]));
+            g_tc.last_estimate = est;
+            if (est <= MATINV_TF32X3_GATE) return MATINV_OK;  // false for NaN
+        }
+        g_tc.last_fallback = 1;
+        g_tc.fallbacks++;
+        flags &= ~MATINV_FLAG_TF32X3;
+    }
+    return invert_dev_once(A_dev, n, X_dev, piv_dev, st, flags);
 }
 
 int ensure_hostio(size_t bytes, size_t ibytes) {
@@ -485,6 +570,31 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
     cudaStream_t st = g.stream;
     CK(cudaMemcpyAsync(g.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(g.ev[0], st));
+    if (flags & MATINV_FLAG_TF32X3) {
+        // gated tensor-core path: A stays in hostio while X is written to a second buffer, then one D2H copy
+        if (g.hostx_bytes < bytes) {
+            cudaFree(g.hostx);
+            g.hostx = nullptr; g.hostx_bytes = 0;
+            CK(cudaMalloc(&g.hostx, bytes));
+            g.hostx_bytes = bytes;
+        }
+        rc = invert_dev_locked(g.hostio, n, g.hostx, piv_host ? g.hostio_i : nullptr, st, flags);
+        if (rc < 0) return rc;
+        CK(cudaEventRecord(g.ev[1], st));
+        if (rc == MATINV_OK) CK(cudaMemcpyAsync(X_host, g.hostx, bytes, cudaMemcpyDeviceToHost, st));
+        if (piv_host) CK(cudaMemcpyAsync(piv_host, g.hostio_i, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+        g_t_compute = ms * 1e-3;
+        g_t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (flags & MATINV_FLAG_VERBOSE) {
+            printf("Tempo Totale Impiegato: %g seconds\n", g_t_total);
+            printf("Tempo Computazione: %g seconds\n", g_t_compute);
+            fflush(stdout);
+        }
+        return rc;
+    }
     rc = factor_locked(g.hostio, n, st, flags);
     if (rc) return rc;
     // extraction (deferred column permutation + isfinite scan) in row chunks, each chunk's D2H copy overlapped with the
@@ -725,6 +835,53 @@ int matinv_debug_trace(int on, long long *out128) {
     if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
     CK(cudaDeviceSynchronize());
     CK(debug_trace(on, out128));
+    return MATINV_OK;
+}
+
+int matinv_tf32x3_status(double *last_estimate, int *last_fallback, long long *inversions, long long *fallbacks) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (last_estimate) *last_estimate = g_tc.last_estimate;
+    if (last_fallback) *last_fallback = g_tc.last_fallback;
+    if (inversions) *inversions = g_tc.inversions;
+    if (fallbacks) *fallbacks = g_tc.fallbacks;
+    return MATINV_OK;
+}
+
+int matinv_debug_trailing_update(float *W_dev, long long ld, int npad, int k0, const float *CmT_dev, const float *U_dev, int mode,
+                                 int reps, double *avg_ms, void *stream) {
+    g_err[0] = 0;
+    if (!W_dev || !CmT_dev || !U_dev || npad < 2 * MATINV_NB || npad % MATINV_NB || k0 < 0 || k0 >= npad || k0 % MATINV_NB ||
+        ld < npad || reps < 1)
+        return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / MATINV_NB, k = k0 / MATINV_NB;
+    float *imgA = nullptr, *imgB = nullptr;
+    if (mode != 0) {
+        CK(cudaMalloc(&imgA, tf32x3_image_bytes(nt)));
+        CK(cudaMalloc(&imgB, tf32x3_image_bytes(nt)));
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    cudaError_t e = cudaSuccess;
+    for (int r = 0; r < reps && e == cudaSuccess; r++) {
+        if (mode == 0) launch_trailing_gemm_ex(W_dev, ld, nt, nt, k, k, 1, MATINV_NB, CmT_dev, ld, U_dev, ld, st);
+        else e = launch_trailing_tf32x3(W_dev, ld, nt, nt, k, k, 1, MATINV_NB, CmT_dev, ld, U_dev, ld, imgA, imgB, st);
+    }
+    cudaEventRecord(e1, st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(imgA);
+    cudaFree(imgB);
+    if (e != cudaSuccess) return fail(MATINV_E_CUDA, "trailing update (mode %d): %s", mode, cudaGetErrorString(e));
+    if (avg_ms) *avg_ms = (double)ms / reps;
     return MATINV_OK;
 }
 

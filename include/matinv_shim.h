@@ -31,11 +31,15 @@ extern "C" {
 #define MATINV_E_UNSUPPORTED (-4)
 
 /* flags */
-#define MATINV_FLAG_TF32X3 1    /* reserved: 3xTF32 tcgen05 trailing update (not bit-exact)      */
+#define MATINV_FLAG_TF32X3 1    /* trailing update as 3xTF32 on tcgen05 tensor cores; NOT bit-exact, accepted only
+                                   if the residual estimate passes MATINV_TF32X3_GATE, else the FP32 path is rerun */
 #define MATINV_FLAG_UNBLOCKED 2 /* force the unblocked 3-kernel-per-column path (parity checks)  */
 #define MATINV_FLAG_VERBOSE 4   /* print the reference's two stdout lines (LIB:385-386)          */
 #define MATINV_FLAG_NOCHECK 8   /* skip the final isfinite scan (kept off the hot path timing)   */
 #define MATINV_FLAG_NOPIVOT 16  /* FP64 entries only: pivot = diagonal entry, no row interchange    */
+
+/* Gate of MATINV_FLAG_TF32X3: estimate of ||A X - I||_F / (n ||A||_F ||X||_F) must not exceed this (north_star bound). */
+#define MATINV_TF32X3_GATE 1e-5
 
 /* Replaces cl::Platform::get / getDevices (LIB:239-244).  Number of usable CUDA devices, 0 if none. */
 int matinv_device_count(void);
@@ -130,6 +134,17 @@ int matinv_last_timing(double *total_s, double *compute_s);
  * algorithmic flops of those launches, and the number of kernels launched in total. */
 void matinv_profile_enable(int on);
 int matinv_profile_read(double *gemm_ms, long long *gemm_launches, double *gemm_flops, long long *all_launches);
+
+/* MATINV_FLAG_TF32X3 bookkeeping: residual estimate of the last gated inversion (-1 if none), whether it fell back to
+ * the FP32 SIMT schedule, and the totals since the library was loaded.  Any pointer may be NULL. */
+int matinv_tf32x3_status(double *last_estimate, int *last_fallback, long long *inversions, long long *fallbacks);
+
+/* Test hook: ONE trailing update  W[i][j] -= sum_t CmT[t][i] U[t][j]  (128 steps) on an npad x npad matrix whose pivot
+ * rows / panel columns are block k0/128; CmT and U are 128 x npad with leading dimension ld.  mode 0 = FP32 SIMT kernel
+ * (gj_gemm.cu), mode 1 = 3xTF32 tcgen05 kernel (gj_gemm_tc.cu).  The update is applied `reps` times back to back; avg_ms (may
+ * be NULL) receives the CUDA-event time per application.  Synchronises the stream. */
+int matinv_debug_trailing_update(float *W_dev, long long ld, int npad, int k0, const float *CmT_dev, const float *U_dev,
+                                 int mode, int reps, double *avg_ms, void *stream);
 
 /* Tuning aid: switch the in-kernel timeline of the panel kernels on/off and read the SM-clock stamps of
  * the last launch (128 slots; see gj_subpanel.cu).  out128 may be NULL. */
