@@ -268,9 +268,213 @@ trailing_tf32x3_kernel(float *__restrict__ W, long long ld, int row_skip, int co
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2 (default): one CTA per SM walks a STRIP of up to `strip` consecutive column tiles of one tile row.
+//   * the A image of the row tile (hi|lo, all K: 128 KiB) is loaded once and stays in shared memory -- v1 re-reads it
+//     for every tile, which doubles the L2 -> SM operand traffic (256 KiB per 128 KiB of W traffic);
+//   * only B streams, through a 4-stage ring of 16 KiB stages (K = 16, hi|lo);
+//   * two TMEM accumulators (2 x 128 columns): the MMAs of tile t+1 run while the epilogue drains tile t;
+//   * the epilogue issues ALL of its W loads for a tile (512 B per thread, 64 KiB per CTA) before it waits for the
+//     accumulator, so a full tile of HBM reads is in flight per SM while the tensor core works, and transposes the
+//     accumulator through shared memory so that W is read and written in 128-byte row segments.
+constexpr int TC2_STAGES = 4;
+constexpr int TC2_STAGE_BYTES = 2 * TC_CHUNK_BYTES;                  // B hi | lo for 16 k: 16 KiB
+constexpr int TC2_A_BYTES = TC_TILE_IMG_FLOATS * 4;                  // 128 KiB
+constexpr unsigned TC2_STAGE_ROW_BYTES = 32 * 4 + 16;               // epilogue patch row: 32 floats + 16 B pad (conflict-free v4 access)
+constexpr int TC2_PATCH_BYTES = 4 * 32 * (int)TC2_STAGE_ROW_BYTES;   // 4 epilogue warps x 32 rows
+constexpr int TC2_SMEM_BYTES = TC2_A_BYTES + TC2_STAGES * TC2_STAGE_BYTES + TC2_PATCH_BYTES + 1024;
+constexpr int TC2_TMEM_COLS = 256;
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, int col_skip, int col_skip_n, int ncols, int strip,
+                             const float *__restrict__ imgA, const float *__restrict__ imgB) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_a, bar_full[TC2_STAGES], bar_empty[TC2_STAGES], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ unsigned tmem_slot;
+
+    int ti = blockIdx.y;
+    ti += (ti >= row_skip);
+    const int x0 = blockIdx.x * strip;                         // logical (skip-free) column tile range of this CTA
+    const int ntiles = min(strip, ncols - x0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned sA = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+    const unsigned ring = sA + TC2_A_BYTES;
+    const unsigned sStage = ring + TC2_STAGES * TC2_STAGE_BYTES;
+
+    if (tid == 0) {
+        mbar_init(&bar_a, 1);
+#pragma unroll
+        for (int s = 0; s < TC2_STAGES; s++) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&bar_acc_full[b], 1);
+            mbar_init(&bar_acc_empty[b], 128);  // every epilogue thread arrives
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"((unsigned)TC2_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *reinterpret_cast<volatile unsigned *>(&tmem_slot);
+
+    if (warp == 1) {
+        // ===== producer
+        if (lane == 0) {
+            const float *ga = imgA + (long long)ti * TC_TILE_IMG_FLOATS;
+            mbar_expect_tx(&bar_a, TC2_A_BYTES);
+#pragma unroll
+            for (int kc = 0; kc < TC_KCH; kc++)
+                bulk_g2s(sA + (unsigned)kc * TC2_STAGE_BYTES, ga + (long long)kc * 2 * TC_CHUNK_FLOATS, TC2_STAGE_BYTES, &bar_a);
+            int it = 0;
+            for (int t = 0; t < ntiles; t++) {
+                int tj = x0 + t;
+                if (col_skip >= 0 && tj >= col_skip) tj += col_skip_n;
+                const float *gb = imgB + (long long)tj * TC_TILE_IMG_FLOATS;
+                for (int kc = 0; kc < TC_KCH; kc++, it++) {
+                    const int s = it % TC2_STAGES;
+                    if (it >= TC2_STAGES) mbar_wait(&bar_empty[s], (unsigned)((it / TC2_STAGES) - 1) & 1u);
+                    mbar_expect_tx(&bar_full[s], TC2_STAGE_BYTES);
+                    bulk_g2s(ring + (unsigned)s * TC2_STAGE_BYTES, gb + (long long)kc * 2 * TC_CHUNK_FLOATS, TC2_STAGE_BYTES, &bar_full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 0) {
+        // ===== MMA issuer
+        if (lane == 0) {
+            mbar_wait(&bar_a, 0);
+            int it = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int b = t & 1;
+                if (t >= 2) mbar_wait(&bar_acc_empty[b], (unsigned)((t >> 1) - 1) & 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const unsigned acc = tmem + (unsigned)b * TC_TILE;
+                for (int kc = 0; kc < TC_KCH; kc++, it++) {
+                    const int s = it % TC2_STAGES;
+                    mbar_wait(&bar_full[s], (unsigned)(it / TC2_STAGES) & 1u);
+                    tc_fence_after();
+                    const unsigned abase = sA + (unsigned)kc * TC2_STAGE_BYTES, bbase = ring + (unsigned)s * TC2_STAGE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ks++) {
+                        const unsigned o = (unsigned)ks * 2u * TC_LBO;
+                        const unsigned long long a_hi = tc_desc(abase + o), a_lo = tc_desc(abase + TC_CHUNK_BYTES + o);
+                        const unsigned long long b_hi = tc_desc(bbase + o), b_lo = tc_desc(bbase + TC_CHUNK_BYTES + o);
+                        tc_mma_tf32(acc, a_lo, b_hi, TC_IDESC, (kc | ks) != 0);
+                        tc_mma_tf32(acc, a_hi, b_lo, TC_IDESC, 1u);
+                        tc_mma_tf32(acc, a_hi, b_hi, TC_IDESC, 1u);
+                    }
+                    tc_commit(&bar_empty[s]);
+                }
+                tc_commit(&bar_acc_full[b]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue.  TMEM hands every lane one ROW of the accumulator; reading and writing W that way would touch 32
+        // different 128-byte lines per instruction.  Each warp therefore transposes its 32 rows through a private, padded
+        // shared-memory patch (32 columns at a time) and accesses W as 4 rows x 128 contiguous bytes per instruction.
+        const int q = warp & 3;
+        const int rsub = lane >> 3, csub = (lane & 7) * 4;
+        const unsigned stage = sStage + (unsigned)q * (32u * TC2_STAGE_ROW_BYTES);
+        float *wbase = W + ((long long)ti * TC_TILE + q * 32 + rsub) * ld + csub;
+        for (int t = 0; t < ntiles; t++) {
+            const int b = t & 1;
+            int tj = x0 + t;
+            if (col_skip >= 0 && tj >= col_skip) tj += col_skip_n;
+            float *wt = wbase + (long long)tj * TC_TILE;
+            float4 c[32];
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++)
+#pragma unroll
+                for (int i = 0; i < 8; i++)  // rows 4i + rsub of this warp's 32, columns 32 ch + csub .. +3: all in flight at once
+                    c[ch * 8 + i] = *reinterpret_cast<const float4 *>(wt + (long long)(4 * i) * ld + 32 * ch);
+            mbar_wait(&bar_acc_full[b], (unsigned)(t >> 1) & 1u);
+            tc_fence_after();
+            const unsigned taddr = tmem + ((unsigned)(q * 32) << 16) + (unsigned)b * TC_TILE;
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                unsigned d[32];
+                tmem_ld32(taddr + (unsigned)(32 * ch), d);
+                tmem_ld_wait();
+#pragma unroll
+                for (int v = 0; v < 8; v++)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (unsigned)lane * TC2_STAGE_ROW_BYTES + 16u * v),
+                                 "r"(d[4 * v]), "r"(d[4 * v + 1]), "r"(d[4 * v + 2]), "r"(d[4 * v + 3])
+                                 : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float4 dd;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(dd.x), "=f"(dd.y), "=f"(dd.z), "=f"(dd.w)
+                                 : "r"(stage + (unsigned)(4 * i + rsub) * TC2_STAGE_ROW_BYTES + 4u * csub)
+                                 : "memory");
+                    const float4 cc = c[ch * 8 + i];
+                    *reinterpret_cast<float4 *>(wt + (long long)(4 * i) * ld + 32 * ch) =
+                        make_float4(cc.x - dd.x, cc.y - dd.y, cc.z - dd.z, cc.w - dd.w);
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_acc_empty[b]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)TC2_TMEM_COLS) : "memory");
+    }
+}
+
 }  // namespace
 
 size_t tf32x3_image_bytes(int tiles) { return (size_t)tiles * TC_TILE_IMG_FLOATS * sizeof(float); }
+
+// MATINV_TC: 1 = one tile per CTA (v1), 2 (default) = strip kernel with resident A and double-buffered accumulator
+static int tc_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MATINV_TC");
+        v = e ? atoi(e) : 2;
+    }
+    return v;
+}
+
+// Tiles per strip: the grid is gy x ceil(gx / L) CTAs at one CTA per SM; pick the L that minimises waves x (L + 1), the +1
+// standing for the once-per-CTA cost (TMEM allocation, the 128 KiB A load).
+static int tc_strip_len(int gx, int gy) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("MATINV_TC_STRIP");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced > 0) return forced < gx ? forced : gx;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int best = 1;
+    long long best_cost = -1;
+    for (int L = 1; L <= 12 && L <= gx; L++) {
+        const long long ctas = (long long)gy * ((gx + L - 1) / L);
+        const long long cost = ((ctas + sms - 1) / sms) * (L + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = L; }
+    }
+    return best;
+}
 
 // Same tile selection as launch_trailing_gemm_ex (gj_gemm.cu).  imgA must hold nrow_tiles tile images, imgB ncol_tiles; both are
 // scratch owned by the caller and must not be shared with a launch that may run concurrently on another stream.
@@ -280,11 +484,19 @@ cudaError_t launch_trailing_tf32x3(float *W, long long ld, int nrow_tiles, int n
     static bool configured[64] = {};
     if (first_use_on_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(trailing_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(trailing_tf32x3_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES);
         if (e != cudaSuccess) return e;
     }
     const int gx = ncol_tiles - (col_skip >= 0 ? col_skip_n : 0), gy = nrow_tiles - 1;
     if (gx <= 0 || gy <= 0) return cudaSuccess;
     tf32_split_kernel<<<nrow_tiles + ncol_tiles, 256, 0, st>>>(CmT, ldc, imgA, nrow_tiles, U, ldu, imgB, kb);
-    trailing_tf32x3_kernel<<<dim3(gx, gy), 192, TC_SMEM_BYTES, st>>>(W, ld, row_skip, col_skip, col_skip_n, imgA, imgB);
+    if (tc_variant() == 1) {
+        trailing_tf32x3_kernel<<<dim3(gx, gy), 192, TC_SMEM_BYTES, st>>>(W, ld, row_skip, col_skip, col_skip_n, imgA, imgB);
+    } else {
+        const int L = tc_strip_len(gx, gy);
+        trailing_tf32x3_strip_kernel<<<dim3((gx + L - 1) / L, gy), 192, TC2_SMEM_BYTES, st>>>(W, ld, row_skip, col_skip, col_skip_n, gx,
+                                                                                             L, imgA, imgB);
+    }
     return cudaGetLastError();
 }
