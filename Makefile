@@ -25,6 +25,11 @@ $(OUT): $(OBJ)
 oracle:
 	gcc -O3 -mfma -mavx2 -ffp-contract=off -fopenmp -fPIC -shared -o oracle/libgj_oracle.so oracle/gj_oracle.c -lm
 
+# bring-up / regression check of the tcgen05 trailing update without Python (runs in seconds on a fresh GPU box)
+tools/tc_check: tools/tc_check.cpp $(OUT) include/matinv_shim.h
+	g++ -O2 -std=c++17 $< -Iinclude -I/usr/local/cuda/include -Lgpu_matrix_inversion_b200 -lmatinv32 -L/usr/local/cuda/lib64 -lcudart \
+	    -Wl,-rpath,'$$ORIGIN/../gpu_matrix_inversion_b200' -Wl,-rpath,/usr/local/cuda/lib64 -o $@
+
 clean:
 	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log $(OUT) oracle/libgj_oracle.so
 

@@ -21,11 +21,12 @@ import numpy as np
 
 __all__ = ["lib", "matrix_inv_32", "invert", "invert_dev", "invert_batched", "invert_batched_dev", "device_count",
            "last_error", "last_timing", "MatinvError", "OK", "SINGULAR", "FLAG_UNBLOCKED", "FLAG_VERBOSE",
-           "FLAG_NOCHECK", "FLAG_TF32X3", "EXPORTS"]
+           "FLAG_NOCHECK", "FLAG_TF32X3", "TF32X3_GATE", "tf32x3_status", "debug_trailing_update", "probe_residual_dev", "EXPORTS"]
 
 OK, SINGULAR = 0, 1
 E_INVALID, E_NODEVICE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
 FLAG_TF32X3, FLAG_UNBLOCKED, FLAG_VERBOSE, FLAG_NOCHECK, FLAG_NOPIVOT = 1, 2, 4, 8, 16
+TF32X3_GATE = 1e-5   # MATINV_TF32X3_GATE (include/matinv_shim.h)
 
 _SO = Path(__file__).resolve().parent / "libmatinv32.so"
 
@@ -38,7 +39,7 @@ EXPORTS = [
     "matinv_shard_apply", "matinv_shard_apply_ex", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
     "matinv_profile_read", "matinv_debug_trace", "matinv_invert_f64", "matinv_invert_f64_dev", "matinv_residual_f64_dev",
-    "matinv_host_defect_f64",
+    "matinv_host_defect_f64", "matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev",
 ]
 
 
@@ -95,6 +96,11 @@ def _load() -> ctypes.CDLL:
     L.matinv_shard_apply_ex.argtypes = [vp, i, vp, vp, i, i]
     L.matinv_shard_apply_ex.restype = i
     L.matinv_shard_status.argtypes = [vp, ip, ip, vp]
+    L.matinv_tf32x3_status.argtypes = [dp, ip, ctypes.POINTER(ll), ctypes.POINTER(ll)]
+    L.matinv_debug_trailing_update.argtypes = [fp, ll, i, i, fp, fp, i, i, dp, vp]
+    L.matinv_probe_residual_f32_dev.argtypes = [fp, fp, i, dp, vp]
+    for name in ("matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev"):
+        getattr(L, name).restype = i
     for name in ("matinv_invert_f32", "matinv_invert_f32_dev", "matinv_invert_batched_f32",
                  "matinv_invert_batched_f32_dev", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
                  "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_shard_create",
@@ -318,6 +324,44 @@ def ffma_peak_tflops() -> float:
     st = torch.cuda.current_stream().cuda_stream
     _check(lib.matinv_ffma_peak_tflops(ctypes.byref(v), ctypes.c_void_p(st)))
     return v.value
+
+
+def probe_residual_dev(A, X):
+    """O(n^2) randomised estimate of ||A X - I||_F / (n ||A||_F ||X||_F) on CUDA tensors (the gate of FLAG_TF32X3)."""
+    import torch
+
+    n = A.shape[0]
+    out = (ctypes.c_double * 3)()
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    with torch.cuda.device(A.device):
+        _check(lib.matinv_probe_residual_f32_dev(_torch_ptr(A), _torch_ptr(X), n, out, ctypes.c_void_p(st)))
+    r2, a2, x2 = out[0], out[1], out[2]
+    return float(np.sqrt(r2) / (n * np.sqrt(a2) * np.sqrt(x2)))
+
+
+def tf32x3_status():
+    """Bookkeeping of the residual-gated 3xTF32 path (FLAG_TF32X3): dict(estimate, fell_back, inversions, fallbacks).
+    `estimate` is the randomised estimate of ||A X - I||_F / (n ||A||_F ||X||_F) of the last gated inversion."""
+    est, fb = ctypes.c_double(), ctypes.c_int()
+    ninv, nfb = ctypes.c_longlong(), ctypes.c_longlong()
+    _check(lib.matinv_tf32x3_status(ctypes.byref(est), ctypes.byref(fb), ctypes.byref(ninv), ctypes.byref(nfb)))
+    return {"estimate": est.value, "fell_back": bool(fb.value), "inversions": ninv.value, "fallbacks": nfb.value}
+
+
+def debug_trailing_update(W, k0: int, CmT, U, mode: int, reps: int = 1):
+    """Test hook: one trailing update W[i][j] -= sum_t CmT[t][i] U[t][j] in place on CUDA tensors (W: (npad, npad),
+    CmT / U: (128, npad)); mode 0 = FP32 SIMT kernel, 1 = 3xTF32 tcgen05 kernel.  Returns the average ms per application."""
+    import torch
+
+    npad = W.shape[0]
+    assert W.is_cuda and W.dtype == torch.float32 and W.is_contiguous() and W.shape == (npad, npad)
+    assert CmT.shape == (128, npad) and U.shape == (128, npad) and CmT.is_contiguous() and U.is_contiguous()
+    ms = ctypes.c_double()
+    st = torch.cuda.current_stream(W.device).cuda_stream
+    with torch.cuda.device(W.device):
+        _check(lib.matinv_debug_trailing_update(_torch_ptr(W), npad, npad, k0, _torch_ptr(CmT), _torch_ptr(U), mode, reps,
+                                                ctypes.byref(ms), ctypes.c_void_p(st)))
+    return ms.value
 
 
 def profile_enable(on: bool = True) -> None:

@@ -14,19 +14,21 @@
 // if the residual estimate passes (matinv_shim.cu: tf32x3 gate) and reruns the FP32 SIMT schedule otherwise.
 //
 // Two launches per trailing update:
-//   tf32_split_kernel       reads the K-major operands CmT[t][i] / U[t][j] once and writes, per 128-row tile, the
-//                           hi and lo parts in the exact shared-memory image tcgen05.mma wants (K-major, no swizzle:
-//                           8x16-byte core matrices, 128 contiguous bytes each), so that the GEMM kernel can stage
-//                           an operand with ONE linear bulk copy and needs no tensor map.  64 MiB at N=16384, L2-resident.
-//   trailing_tf32x3_kernel  one 128x128 tile of W per CTA, 192 threads, 2 CTAs per SM:
-//                             warp 0   allocates 128 TMEM columns; lane 0 issues the MMAs (6 per 16-deep K stage)
-//                             warp 1   lane 0 = producer: cp.async.bulk (TMA, linear) into a 3-stage 32 KiB ring,
-//                                      completion on mbarriers; slots are released by tcgen05.commit
-//                             warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns), W - D, store
+//   tf32_split_kernel             reads the K-major operands CmT[t][i] / U[t][j] once and writes, per 128-row tile, the hi and
+//                                 lo parts in the exact shared-memory image tcgen05.mma wants (K-major, no swizzle: 8 x 16-byte
+//                                 core matrices, 128 contiguous bytes each), so the GEMM kernel stages an operand with linear
+//                                 bulk copies and needs no tensor map.  2 x 16 MiB at N=16384, L2-resident.
+//   trailing_tf32x3_strip_kernel  one CTA per SM, 192 threads, a strip of column tiles of one tile row per CTA (see below):
+//                                   warp 0     allocates 256 TMEM columns; lane 0 issues the MMAs (6 per 16-deep K stage)
+//                                   warp 1     lane 0 = producer: cp.async.bulk (TMA, linear) -- the A image once, B through a
+//                                              4-slot ring; completion on mbarriers, slots released by tcgen05.commit
+//                                   warps 2-5  epilogue: tcgen05.ld -> shared-memory transpose -> W - D in 128-byte row segments
 //
-// What bounds it: 2 * 64 KiB of W traffic per tile against 3 * 2*128^3 tensor flops -- at the measured 6.4 TB/s the
-// W traffic of one trailing update at N=16384 (2.1 GB) takes 0.33 ms, the 3xTF32 MMAs 0.18 ms at the nominal TF32 peak:
-// HBM-bound, where the FP32 SIMT kernel is FP32-pipe-bound at 1.2 ms.
+// What bounds it: 2 x 64 KiB of W traffic per tile against 3 x 2 x 128^3 tensor flops -- at the measured 6.4 TB/s the W
+// traffic of one trailing update at N=16384 (2.1 GB) takes 0.33 ms, the 3xTF32 MMAs 0.18 ms at the nominal TF32 peak:
+// HBM-bound, where the FP32 SIMT kernel is FP32-pipe-bound at 1.19 ms.  Measured: 0.55 ms = 3.85 TB/s of W traffic (60 % of
+// the HBM peak).  History on B200: one tile per CTA with both operands re-read per tile and a row-per-lane epilogue 0.92 ms;
+// resident A + double-buffered accumulator 0.76 ms; coalesced epilogue 0.55 ms.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -37,13 +39,9 @@ namespace {
 constexpr int TC_TILE = 128;                           // tile edge == panel width == MMA M == MMA N
 constexpr int TC_BK = 16;                              // K per pipeline stage (2 MMA k-steps of 8)
 constexpr int TC_KCH = 128 / TC_BK;                    // stages per tile
-constexpr int TC_STAGES = 3;                           // ring depth
 constexpr int TC_CHUNK_FLOATS = TC_TILE * TC_BK;       // one operand part (hi or lo) of one stage: 2048 floats
 constexpr int TC_CHUNK_BYTES = TC_CHUNK_FLOATS * 4;    // 8 KiB
-constexpr int TC_STAGE_BYTES = 4 * TC_CHUNK_BYTES;     // A_hi | A_lo | B_hi | B_lo = 32 KiB
 constexpr int TC_TILE_IMG_FLOATS = TC_KCH * 2 * TC_CHUNK_FLOATS;  // image of one 128-row tile, all K: 128 KiB
-constexpr int TC_TMEM_COLS = 128;                      // 128 x 128 FP32 accumulator
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;  // + slack to align the ring to 1 KiB
 
 // Inside one 8 KiB chunk (128 rows x 16 k, K-major, no swizzle): core matrix = 8 rows x 16 bytes (4 TF32), stored as 128
 // contiguous bytes; the 16 row groups of one 4-wide K slice follow each other (SBO = 128 B), the 4 K slices are 2 KiB
@@ -159,138 +157,28 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&d)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192, 2)
-trailing_tf32x3_kernel(float *__restrict__ W, long long ld, int row_skip, int col_skip, int col_skip_n,
-                       const float *__restrict__ imgA, const float *__restrict__ imgB) {
-    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    __shared__ __align__(8) unsigned long long bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_done;
-    __shared__ unsigned tmem_slot;
-
-    int tj = blockIdx.x, ti = blockIdx.y;
-    if (col_skip >= 0 && tj >= col_skip) tj += col_skip_n;  // the panel's tile column(s)
-    ti += (ti >= row_skip);                                 // the pivot rows' tile row
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned ring = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < TC_STAGES; s++) {
-            mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1);
-        }
-        mbar_init(&bar_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {  // whole warp: TMEM allocation, base address lands in shared memory
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                     "r"((unsigned)TC_TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const unsigned tmem = *reinterpret_cast<volatile unsigned *>(&tmem_slot);
-
-    if (warp == 1) {
-        // ===== producer: two 16 KiB linear bulk copies per stage (A hi|lo, B hi|lo)
-        if (lane == 0) {
-            const float *ga = imgA + (long long)ti * TC_TILE_IMG_FLOATS;
-            const float *gb = imgB + (long long)tj * TC_TILE_IMG_FLOATS;
-            for (int kc = 0; kc < TC_KCH; kc++) {
-                const int s = kc % TC_STAGES;
-                if (kc >= TC_STAGES) mbar_wait(&bar_empty[s], (unsigned)((kc / TC_STAGES) - 1) & 1u);
-                mbar_expect_tx(&bar_full[s], TC_STAGE_BYTES);
-                const unsigned dst = ring + (unsigned)s * TC_STAGE_BYTES;
-                bulk_g2s(dst, ga + (long long)kc * 2 * TC_CHUNK_FLOATS, 2 * TC_CHUNK_BYTES, &bar_full[s]);
-                bulk_g2s(dst + 2 * TC_CHUNK_BYTES, gb + (long long)kc * 2 * TC_CHUNK_FLOATS, 2 * TC_CHUNK_BYTES, &bar_full[s]);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 0) {
-        // ===== MMA issuer: per 8-deep k-step  D += A_lo*B_hi ; D += A_hi*B_lo ; D += A_hi*B_hi
-        if (lane == 0) {
-            for (int kc = 0; kc < TC_KCH; kc++) {
-                const int s = kc % TC_STAGES;
-                mbar_wait(&bar_full[s], (unsigned)(kc / TC_STAGES) & 1u);
-                tc_fence_after();
-                const unsigned base = ring + (unsigned)s * TC_STAGE_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < TC_BK / 8; ks++) {
-                    const unsigned o = (unsigned)ks * 2u * TC_LBO;  // 8 k = two 4-wide K slices
-                    const unsigned long long a_hi = tc_desc(base + o), a_lo = tc_desc(base + TC_CHUNK_BYTES + o);
-                    const unsigned long long b_hi = tc_desc(base + 2 * TC_CHUNK_BYTES + o), b_lo = tc_desc(base + 3 * TC_CHUNK_BYTES + o);
-                    tc_mma_tf32(tmem, a_lo, b_hi, TC_IDESC, (kc | ks) != 0);
-                    tc_mma_tf32(tmem, a_hi, b_lo, TC_IDESC, 1u);
-                    tc_mma_tf32(tmem, a_hi, b_hi, TC_IDESC, 1u);
-                }
-                tc_commit(&bar_empty[s]);  // slot free once these MMAs have read it
-            }
-            tc_commit(&bar_done);          // accumulator complete
-        }
-        __syncwarp();
-    } else {
-        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; lane l owns row 32*(w%4) + l of the tile
-        const int q = warp & 3;
-        float *row = W + ((long long)ti * TC_TILE + q * 32 + lane) * ld + (long long)tj * TC_TILE;
-        const unsigned taddr = tmem + ((unsigned)(q * 32) << 16);
-        float4 c[8], cn[8];
-#pragma unroll
-        for (int v = 0; v < 8; v++) c[v] = *reinterpret_cast<const float4 *>(row + 4 * v);  // in flight during the MMAs
-        mbar_wait(&bar_done, 0);
-        tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < TC_TILE; c0 += 32) {
-            unsigned d[32];
-            tmem_ld32(taddr + (unsigned)c0, d);
-            if (c0 + 32 < TC_TILE) {
-#pragma unroll
-                for (int v = 0; v < 8; v++) cn[v] = *reinterpret_cast<const float4 *>(row + c0 + 32 + 4 * v);
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int v = 0; v < 8; v++) {
-                float4 o;
-                o.x = c[v].x - __uint_as_float(d[4 * v + 0]);
-                o.y = c[v].y - __uint_as_float(d[4 * v + 1]);
-                o.z = c[v].z - __uint_as_float(d[4 * v + 2]);
-                o.w = c[v].w - __uint_as_float(d[4 * v + 3]);
-                *reinterpret_cast<float4 *>(row + c0 + 4 * v) = o;
-            }
-#pragma unroll
-            for (int v = 0; v < 8; v++) c[v] = cn[v];
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)TC_TMEM_COLS) : "memory");
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// v2 (default): one CTA per SM walks a STRIP of up to `strip` consecutive column tiles of one tile row.
-//   * the A image of the row tile (hi|lo, all K: 128 KiB) is loaded once and stays in shared memory -- v1 re-reads it
-//     for every tile, which doubles the L2 -> SM operand traffic (256 KiB per 128 KiB of W traffic);
+// One CTA per SM walks a STRIP of up to `strip` consecutive column tiles of one tile row.
+//   * the A image of the row tile (hi|lo, all K: 128 KiB) is loaded once and stays in shared memory -- re-reading it
+//     for every tile doubles the L2 -> SM operand traffic (256 KiB per 128 KiB of W traffic);
 //   * only B streams, through a 4-stage ring of 16 KiB stages (K = 16, hi|lo);
 //   * two TMEM accumulators (2 x 128 columns): the MMAs of tile t+1 run while the epilogue drains tile t;
 //   * the epilogue issues ALL of its W loads for a tile (512 B per thread, 64 KiB per CTA) before it waits for the
 //     accumulator, so a full tile of HBM reads is in flight per SM while the tensor core works, and transposes the
 //     accumulator through shared memory so that W is read and written in 128-byte row segments.
-constexpr int TC2_STAGES = 4;
 constexpr int TC2_STAGE_BYTES = 2 * TC_CHUNK_BYTES;                  // B hi | lo for 16 k: 16 KiB
 constexpr int TC2_A_BYTES = TC_TILE_IMG_FLOATS * 4;                  // 128 KiB
 constexpr unsigned TC2_STAGE_ROW_BYTES = 32 * 4 + 16;               // epilogue patch row: 32 floats + 16 B pad (conflict-free v4 access)
-constexpr int TC2_PATCH_BYTES = 4 * 32 * (int)TC2_STAGE_ROW_BYTES;   // 4 epilogue warps x 32 rows
-constexpr int TC2_SMEM_BYTES = TC2_A_BYTES + TC2_STAGES * TC2_STAGE_BYTES + TC2_PATCH_BYTES + 1024;
+constexpr int TC2_PATCH_BYTES = 32 * (int)TC2_STAGE_ROW_BYTES;       // per epilogue warp: 32 rows
+// GROUPS epilogue warp-groups of 4 warps (group g drains accumulator g, i.e. tiles t = g mod 2), STAGES ring slots for B
+constexpr int tc2_smem_bytes(int groups, int stages) { return TC2_A_BYTES + stages * TC2_STAGE_BYTES + groups * 4 * TC2_PATCH_BYTES + 1024; }
 constexpr int TC2_TMEM_COLS = 256;
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1)
+template <int GROUPS, int TC2_STAGES>
+__global__ void __launch_bounds__(64 + 128 * GROUPS, 1)
 trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, int col_skip, int col_skip_n, int ncols, int strip,
                              const float *__restrict__ imgA, const float *__restrict__ imgB) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
@@ -387,11 +275,11 @@ trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, 
         // ===== epilogue.  TMEM hands every lane one ROW of the accumulator; reading and writing W that way would touch 32
         // different 128-byte lines per instruction.  Each warp therefore transposes its 32 rows through a private, padded
         // shared-memory patch (32 columns at a time) and accesses W as 4 rows x 128 contiguous bytes per instruction.
-        const int q = warp & 3;
+        const int q = warp & 3, ew = warp - 2, grp = ew >> 2;
         const int rsub = lane >> 3, csub = (lane & 7) * 4;
-        const unsigned stage = sStage + (unsigned)q * (32u * TC2_STAGE_ROW_BYTES);
+        const unsigned stage = sStage + (unsigned)ew * TC2_PATCH_BYTES;
         float *wbase = W + ((long long)ti * TC_TILE + q * 32 + rsub) * ld + csub;
-        for (int t = 0; t < ntiles; t++) {
+        for (int t = grp; t < ntiles; t += GROUPS) {
             const int b = t & 1;
             int tj = x0 + t;
             if (col_skip >= 0 && tj >= col_skip) tj += col_skip_n;
@@ -444,18 +332,11 @@ trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, 
 
 size_t tf32x3_image_bytes(int tiles) { return (size_t)tiles * TC_TILE_IMG_FLOATS * sizeof(float); }
 
-// MATINV_TC: 1 = one tile per CTA (v1), 2 (default) = strip kernel with resident A and double-buffered accumulator
-static int tc_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("MATINV_TC");
-        v = e ? atoi(e) : 2;
-    }
-    return v;
-}
-
-// Tiles per strip: the grid is gy x ceil(gx / L) CTAs at one CTA per SM; pick the L that minimises waves x (L + 1), the +1
-// standing for the once-per-CTA cost (TMEM allocation, the 128 KiB A load).
+// Tiles per strip.  Long strips amortise the once-per-CTA cost (TMEM allocation, the 128 KiB A load) but every kernel of the
+// look-ahead panel chain on the high-priority stream has to wait until running CTAs retire, so short-lived CTAs matter while
+// that chain is the critical path.  Measured on B200 (profiles/README.md): N=16384 strip 1/2/3/4/5/8/12 -> 124.7/107.9/104.8/
+// 106.7/108.9/112.3/114.3 ms; N=32768 strip 2/4/8 -> 782/733/706 ms (there the update dominates).  Above 128 tile rows the
+// length minimises waves x (L + 1).  MATINV_TC_STRIP overrides.
 static int tc_strip_len(int gx, int gy) {
     static int forced = -2;
     if (forced == -2) {
@@ -463,6 +344,7 @@ static int tc_strip_len(int gx, int gy) {
         forced = e ? atoi(e) : -1;
     }
     if (forced > 0) return forced < gx ? forced : gx;
+    if (gy <= 128) return gx < 3 ? gx : 3;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -483,20 +365,17 @@ cudaError_t launch_trailing_tf32x3(float *W, long long ld, int nrow_tiles, int n
                                    cudaStream_t st) {
     static bool configured[64] = {};
     if (first_use_on_device(configured)) {
-        cudaError_t e = cudaFuncSetAttribute(trailing_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(trailing_tf32x3_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(trailing_tf32x3_strip_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             tc2_smem_bytes(1, 4));
         if (e != cudaSuccess) return e;
     }
     const int gx = ncol_tiles - (col_skip >= 0 ? col_skip_n : 0), gy = nrow_tiles - 1;
     if (gx <= 0 || gy <= 0) return cudaSuccess;
     tf32_split_kernel<<<nrow_tiles + ncol_tiles, 256, 0, st>>>(CmT, ldc, imgA, nrow_tiles, U, ldu, imgB, kb);
-    if (tc_variant() == 1) {
-        trailing_tf32x3_kernel<<<dim3(gx, gy), 192, TC_SMEM_BYTES, st>>>(W, ld, row_skip, col_skip, col_skip_n, imgA, imgB);
-    } else {
-        const int L = tc_strip_len(gx, gy);
-        trailing_tf32x3_strip_kernel<<<dim3((gx + L - 1) / L, gy), 192, TC2_SMEM_BYTES, st>>>(W, ld, row_skip, col_skip, col_skip_n, gx,
-                                                                                             L, imgA, imgB);
-    }
+    const int L = tc_strip_len(gx, gy);
+    // <2, 3> (a second epilogue warp-group, one per accumulator) was measured slower: 0.607 vs 0.550 ms per update at N=16384
+    // (320 threads cap the epilogue at 168 registers and spill)
+    trailing_tf32x3_strip_kernel<1, 4><<<dim3((gx + L - 1) / L, gy), 192, tc2_smem_bytes(1, 4), st>>>(W, ld, row_skip, col_skip,
+                                                                                                     col_skip_n, gx, L, imgA, imgB);
     return cudaGetLastError();
 }

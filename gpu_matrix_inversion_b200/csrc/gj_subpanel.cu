@@ -546,6 +546,11 @@ static cudaError_t launch_subpanel_t(int ncta, const float *in, long long ld_in,
     return cudaLaunchKernelEx(&cfg, subpanel_kernel<W, R, TH>, in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info);
 }
 
+// Set by the shim while the trailing update runs on the tensor cores (MATINV_FLAG_TF32X3): the update is then ~2x shorter,
+// the panel chain is the critical path at every n, and the shapes tuned for "fast" win over the shapes tuned for "small".
+static int g_panel_critical = 0;
+void panel_set_critical(int on) { g_panel_critical = on; }
+
 int subpanel_width(int n) { return (n > 32768) ? 8 : 16; }
 bool subpanel_supported(int n) { return n <= 65536; }
 
@@ -570,7 +575,7 @@ cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long l
             const char *e = getenv("MATINV_K1_THREADS");
             forced = e ? atoi(e) : 0;
         }
-        const int th = forced ? forced : (n >= 15360 ? 256 : 512);
+        const int th = forced ? forced : ((n >= 15360 && !g_panel_critical) ? 256 : 512);
         if (th == 256) return launch_subpanel_t<16, 4, 256>(16, SP_ARGS);
         return launch_subpanel_t<16, 2, 512>(16, SP_ARGS);
     }
@@ -603,7 +608,7 @@ void launch_panel_update(const float *in, long long ld_in, float *out, long long
         const char *e = getenv("MATINV_UPDATE_ROWS");
         forced = e ? atoi(e) : 0;
     }
-    const int rows = forced ? forced : (n <= 11264 ? 64 : 256);
+    const int rows = forced ? forced : ((n <= 11264 || g_panel_critical) ? 64 : 256);
     if (rows == 64) launch_panel_update_t<64>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
     else if (rows == 128) launch_panel_update_t<128>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);
     else if (rows == 512) launch_panel_update_t<512>(in, ld_in, out, ld_out, n, k0, s0, sw, wfull, CmT, ldc, piv, pv, ps, kb, st);

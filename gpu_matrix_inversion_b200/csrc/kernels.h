@@ -37,6 +37,7 @@ void launch_panel_step(const float *in, long long ld_in, float *out, long long l
 
 // ---- gj_subpanel.cu : panel factorisation v1 (cluster/DSMEM sub-panel kernel + in-panel update)
 int subpanel_width(int n);
+void panel_set_critical(int on);
 bool subpanel_supported(int n);
 cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0,
                             int sw, float *CmT, long long ldc, int *piv, float *pv, int *info, cudaStream_t st);

@@ -429,16 +429,18 @@ int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags) {
         rc = ensure_tc(w);
         if (rc) return rc;
         g_tc.on = g_tc.used = true;
+        panel_set_critical(1);
     }
     CK(cudaMemsetAsync(w.info, 0, sizeof(int), st));
     launch_load(A_dev, n, w.W, npad, npad, st);
     if (flags & MATINV_FLAG_UNBLOCKED) schedule_unblocked(w, n, st);
     else if (use_lookahead(n, npad)) {
         rc = ensure_lookahead();
-        if (rc) { g_tc.on = false; return rc; }
+        if (rc) { g_tc.on = false; panel_set_critical(0); return rc; }
         schedule_lookahead(w, n, st);
     } else schedule_blocked(w, n, st);
     g_tc.on = false;
+    panel_set_critical(0);
     COUNT_LAUNCH(3);
     launch_colperm_build(w.piv, n, w.colsrc, st);
     CK(cudaGetLastError());
@@ -835,6 +837,19 @@ int matinv_debug_trace(int on, long long *out128) {
     if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
     CK(cudaDeviceSynchronize());
     CK(debug_trace(on, out128));
+    return MATINV_OK;
+}
+
+int matinv_probe_residual_f32_dev(const float *A_dev, const float *X_dev, int n, double *out_host, void *stream) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_dev || !X_dev || !out_host) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    double *scratch = nullptr;
+    CK(cudaMalloc(&scratch, probe_scratch_bytes(n)));
+    const cudaError_t e = run_probe_residual(A_dev, X_dev, n, scratch, out_host, (cudaStream_t)stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail(MATINV_E_CUDA, "probe residual: %s", cudaGetErrorString(e));
     return MATINV_OK;
 }
 

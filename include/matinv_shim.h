@@ -135,6 +135,10 @@ int matinv_last_timing(double *total_s, double *compute_s);
 void matinv_profile_enable(int on);
 int matinv_profile_read(double *gemm_ms, long long *gemm_launches, double *gemm_flops, long long *all_launches);
 
+/* O(n^2) randomised estimate of the same three numbers (4 Rademacher probe vectors: E ||(A X - I) v||^2 = ||A X - I||_F^2);
+ * out_host[0] is an estimate, out_host[1..2] are exact.  This is what gates MATINV_FLAG_TF32X3. */
+int matinv_probe_residual_f32_dev(const float *A_dev, const float *X_dev, int n, double *out_host, void *stream);
+
 /* MATINV_FLAG_TF32X3 bookkeeping: residual estimate of the last gated inversion (-1 if none), whether it fell back to
  * the FP32 SIMT schedule, and the totals since the library was loaded.  Any pointer may be NULL. */
 int matinv_tf32x3_status(double *last_estimate, int *last_fallback, long long *inversions, long long *fallbacks);

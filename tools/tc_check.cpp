@@ -104,9 +104,11 @@ static int pattern_test(Dev &d, const char *name, int kk, int amode, int bmode) 
 
 int main(int argc, char **argv) {
     const int big = (argc > 1) ? atoi(argv[1]) : 16384;
+    const bool inv_only = argc > 2 && !strcmp(argv[2], "inv");  // only section 4 at n = big
     if (matinv_device_count() <= 0) { printf("no CUDA device\n"); return 1; }
     int fails = 0;
     Dev d;
+    if (!inv_only) {
     d.alloc(512);
     // ---- 1. patterns
     const int kks[] = {0, 1, 3, 4, 7, 8, 15, 16, 17, 127};
@@ -173,9 +175,11 @@ int main(int argc, char **argv) {
         d.release();
     }
 
+    }
     // ---- 4. whole inversions
     const int sizes[] = {1024, 4096, big};
     for (int n : sizes) {
+        if (inv_only && n != big) continue;
         float *A = nullptr, *X = nullptr;
         int *piv = nullptr;
         CUDA_OK(cudaMalloc(&A, (size_t)n * n * 4));
