@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(64 + 128 * GROUPS, 1)
 trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, int col_skip, int col_skip_n, int ncols, int strip,
                              const float *__restrict__ imgA, const float *__restrict__ imgB) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    __shared__ __align__(8) unsigned long long bar_a, bar_full[TC2_STAGES], bar_empty[TC2_STAGES], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ __align__(8) unsigned long long bar_a[TC_KCH], bar_full[TC2_STAGES], bar_empty[TC2_STAGES], bar_acc_full[2], bar_acc_empty[2];
     __shared__ unsigned tmem_slot;
 
     int ti = blockIdx.y;
@@ -195,7 +195,8 @@ trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, 
     const unsigned sStage = ring + TC2_STAGES * TC2_STAGE_BYTES;
 
     if (tid == 0) {
-        mbar_init(&bar_a, 1);
+#pragma unroll
+        for (int kc = 0; kc < TC_KCH; kc++) mbar_init(&bar_a[kc], 1);
 #pragma unroll
         for (int s = 0; s < TC2_STAGES; s++) {
             mbar_init(&bar_full[s], 1);
@@ -223,10 +224,6 @@ trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, 
         // ===== producer
         if (lane == 0) {
             const float *ga = imgA + (long long)ti * TC_TILE_IMG_FLOATS;
-            mbar_expect_tx(&bar_a, TC2_A_BYTES);
-#pragma unroll
-            for (int kc = 0; kc < TC_KCH; kc++)
-                bulk_g2s(sA + (unsigned)kc * TC2_STAGE_BYTES, ga + (long long)kc * 2 * TC_CHUNK_FLOATS, TC2_STAGE_BYTES, &bar_a);
             int it = 0;
             for (int t = 0; t < ntiles; t++) {
                 int tj = x0 + t;
@@ -234,6 +231,11 @@ trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, 
                 const float *gb = imgB + (long long)tj * TC_TILE_IMG_FLOATS;
                 for (int kc = 0; kc < TC_KCH; kc++, it++) {
                     const int s = it % TC2_STAGES;
+                    if (t == 0) {  // the resident A image travels chunk by chunk next to the first tile's B stages, one
+                                   // barrier per chunk, so the first MMAs start after 32 KiB instead of 144 KiB
+                        mbar_expect_tx(&bar_a[kc], TC2_STAGE_BYTES);
+                        bulk_g2s(sA + (unsigned)kc * TC2_STAGE_BYTES, ga + (long long)kc * 2 * TC_CHUNK_FLOATS, TC2_STAGE_BYTES, &bar_a[kc]);
+                    }
                     if (it >= TC2_STAGES) mbar_wait(&bar_empty[s], (unsigned)((it / TC2_STAGES) - 1) & 1u);
                     mbar_expect_tx(&bar_full[s], TC2_STAGE_BYTES);
                     bulk_g2s(ring + (unsigned)s * TC2_STAGE_BYTES, gb + (long long)kc * 2 * TC_CHUNK_FLOATS, TC2_STAGE_BYTES, &bar_full[s]);
@@ -244,7 +246,6 @@ trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, 
     } else if (warp == 0) {
         // ===== MMA issuer
         if (lane == 0) {
-            mbar_wait(&bar_a, 0);
             int it = 0;
             for (int t = 0; t < ntiles; t++) {
                 const int b = t & 1;
@@ -253,6 +254,7 @@ trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, 
                 const unsigned acc = tmem + (unsigned)b * TC_TILE;
                 for (int kc = 0; kc < TC_KCH; kc++, it++) {
                     const int s = it % TC2_STAGES;
+                    if (t == 0) mbar_wait(&bar_a[kc], 0);
                     mbar_wait(&bar_full[s], (unsigned)(it / TC2_STAGES) & 1u);
                     tc_fence_after();
                     const unsigned abase = sA + (unsigned)kc * TC2_STAGE_BYTES, bbase = ring + (unsigned)s * TC2_STAGE_BYTES;

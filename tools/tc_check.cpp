@@ -104,7 +104,8 @@ static int pattern_test(Dev &d, const char *name, int kk, int amode, int bmode) 
 
 int main(int argc, char **argv) {
     const int big = (argc > 1) ? atoi(argv[1]) : 16384;
-    const bool inv_only = argc > 2 && !strcmp(argv[2], "inv");  // only section 4 at n = big
+    const bool tc_only = argc > 2 && !strcmp(argv[2], "tc");    // only the tf32x3 inversion at n = big (profiling runs)
+    const bool inv_only = tc_only || (argc > 2 && !strcmp(argv[2], "inv"));  // only section 4 at n = big
     if (matinv_device_count() <= 0) { printf("no CUDA device\n"); return 1; }
     int fails = 0;
     Dev d;
@@ -187,7 +188,7 @@ int main(int argc, char **argv) {
         CUDA_OK(cudaMalloc(&piv, (size_t)n * 4));
         matinv_generate_f32_dev(A, n, n, 0xB2000000ull + n, 0, 0, n, nullptr);
         std::vector<int> p0(n), p1(n);
-        for (int pass = 0; pass < 2; pass++) {
+        for (int pass = tc_only ? 1 : 0; pass < 2; pass++) {
             const int flags = pass ? MATINV_FLAG_TF32X3 : 0;
             int rc = matinv_invert_f32_dev(A, n, X, piv, nullptr, flags);  // warm-up (allocations)
             const auto t0 = std::chrono::steady_clock::now();
