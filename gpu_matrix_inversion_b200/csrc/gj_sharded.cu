@@ -97,6 +97,7 @@ int matinv_shard_create(int n, int rank, int world, matinv_shard_t **out) {
     if (e == cudaSuccess) e = cudaMemset(s->P[1], 0, N * MATINV_NB * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(s->piv, 0, N * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(s->info, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();  // null-stream memsets vs the caller's non-blocking streams
     if (e != cudaSuccess) {
         matinv_shard_destroy(s);
         return shim_fail(MATINV_E_CUDA, "shard allocation failed: %s", cudaGetErrorString(e));

@@ -188,6 +188,9 @@ int ensure_ws(int npad) {
     CK(cudaMemset(w.U, 0, MATINV_NB * N * sizeof(float)));
     CK(cudaMemset(w.P[0], 0, N * MATINV_NB * sizeof(float)));
     CK(cudaMemset(w.P[1], 0, N * MATINV_NB * sizeof(float)));
+    // the memsets run on the legacy default stream, the kernels on non-blocking streams that do not order against it: without
+    // this a memset could land AFTER the first panel kernel had written P[0] (seen as X = 0 for n <= 16 right after a resize)
+    CK(cudaDeviceSynchronize());
     w.npad = npad;
     return 0;
 }
