@@ -15,15 +15,17 @@
 
 namespace {
 
-constexpr int PROBES = 4;
+constexpr int PROBES = 4;   // the pass-2 loads below are written for 4 (two double2 per index)
 
-__device__ __forceinline__ double probe_sign(int j, int p) {
-    u64 z = ((u64)j * PROBES + (u64)p) + 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (z >> 63) ? -1.0 : 1.0;
+// PROBES sign bits per index from one 32-bit integer hash (lowbias32 finaliser): bit p set -> v_p[j] = -1
+__device__ __forceinline__ unsigned probe_bits(int j) {
+    unsigned x = (unsigned)j * 0x9E3779B9u + 0x85EBCA6Bu;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x >> (32 - PROBES);
 }
+__device__ __forceinline__ double probe_sign(unsigned bits, int p) { return ((bits >> p) & 1u) ? -1.0 : 1.0; }
 
 // out[0] += sum of squares of M;  PASS 1: Y[i][p] = sum_j M[i][j] v_p[j];  PASS 2: out[1] += sum_p (sum_j M[i][j] Y[j][p] - v_p[i])^2
 template <int PASS>
@@ -34,11 +36,22 @@ __global__ void __launch_bounds__(256) probe_kernel(const float *__restrict__ M,
     if (i >= n) return;
     const float *row = M + (long long)i * n;
     double acc[PROBES] = {}, sq = 0.0;
+#pragma unroll 4
     for (int j = lane; j < n; j += 32) {
         const double m = (double)row[j];
         sq = fma(m, m, sq);
+        if (PASS == 1) {
+            const unsigned bits = probe_bits(j);
 #pragma unroll
-        for (int p = 0; p < PROBES; p++) acc[p] = fma(m, PASS == 1 ? probe_sign(j, p) : Y[(long long)j * PROBES + p], acc[p]);
+            for (int p = 0; p < PROBES; p++) acc[p] += ((bits >> p) & 1u) ? -m : m;
+        } else {
+            const double2 y01 = *reinterpret_cast<const double2 *>(Y + (long long)j * PROBES);
+            const double2 y23 = *reinterpret_cast<const double2 *>(Y + (long long)j * PROBES + 2);
+            acc[0] = fma(m, y01.x, acc[0]);
+            acc[1] = fma(m, y01.y, acc[1]);
+            acc[2] = fma(m, y23.x, acc[2]);
+            acc[3] = fma(m, y23.y, acc[3]);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -52,10 +65,11 @@ __global__ void __launch_bounds__(256) probe_kernel(const float *__restrict__ M,
 #pragma unroll
             for (int p = 0; p < PROBES; p++) Y[(long long)i * PROBES + p] = acc[p];
         } else {
+            const unsigned bits = probe_bits(i);
             double r2 = 0.0;
 #pragma unroll
             for (int p = 0; p < PROBES; p++) {
-                const double z = acc[p] - probe_sign(i, p);
+                const double z = acc[p] - probe_sign(bits, p);
                 r2 = fma(z, z, r2);
             }
             atomicAdd(&out[1], r2 / PROBES);
