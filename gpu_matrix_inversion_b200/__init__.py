@@ -158,8 +158,9 @@ def matrix_inv_32(matrix_vector, matrix_order: int) -> np.ndarray:
     n = int(matrix_order)
     if n <= 0 or v.size // n != n:
         return np.empty(0, dtype=np.float32)
+    flags = FLAG_TF32X3 if os.environ.get("MATINV_TF32X3", "0") not in ("", "0") else 0   # same opt-in as mat_inv_32.cpp
     try:
-        X = invert(v[: n * n].reshape(n, n))
+        X = invert(v[: n * n].reshape(n, n), flags=flags)
     except MatinvError:
         return np.empty(0, dtype=np.float32)
     return np.empty(0, dtype=np.float32) if X is None else X.ravel()

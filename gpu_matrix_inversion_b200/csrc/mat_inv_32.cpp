@@ -33,6 +33,10 @@ std::vector<float> matrix_inv_32(std::vector<float> matrix_vector, int matrix_or
     int flags = 0;
     const char *verbose = std::getenv("MATINV_VERBOSE");
     if (verbose && verbose[0] && verbose[0] != '0') flags |= MATINV_FLAG_VERBOSE;
+    // opt-in, off by default: trailing updates on the tensor cores (3xTF32, residual-gated, not bit-identical to the
+    // reference's FMA chain) -- the signature clibgen binds cannot carry a flag, so the switch is an environment variable
+    const char *tc = std::getenv("MATINV_TF32X3");
+    if (tc && tc[0] && tc[0] != '0') flags |= MATINV_FLAG_TF32X3;
     const int rc = matinv_invert_f32(matrix_vector.data(), matrix_order, result.data(), nullptr, flags);
     if (rc == MATINV_OK) return result;
     if (rc < 0) std::cerr << "ERRORE N\xC2\xB0: " << rc << " (" << matinv_last_error() << ")" << std::endl;  // LIB:392
