@@ -330,6 +330,142 @@ trailing_tf32x3_strip_kernel(float *__restrict__ W, long long ld, int row_skip, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL alternative (MATINV_TC_KERNEL=tile; NOT the default, see DESIGN section 10 "what bounds it"): one 128x128 tile
+// per CTA, TWO CTAs per SM, both operands streamed through a deeper ring of small stages.  The strip kernel keeps A
+// resident, which leaves shared memory for only 64 KiB of B in flight per SM; here nothing is resident, a stage is 8 k
+// of all four operand parts (4 x 4 KiB), five slots per CTA -> 160 KiB in flight per SM, and the second CTA's main loop
+// overlaps the first one's epilogue instead of a second accumulator.  CTAs live for one tile, which also lets the
+// look-ahead panel chain find free SMs sooner.  Costs: A is re-read from L2 for every tile (2 x the operand traffic).
+constexpr int TC3_STAGES = 5;
+constexpr int TC3_BK = 8;                                  // one MMA k-step per stage
+constexpr int TC3_PART_BYTES = TC_TILE * TC3_BK * 4;       // one operand part: 128 rows x 8 k = 4 KiB (two 4-wide K slices)
+constexpr int TC3_STAGE_BYTES = 4 * TC3_PART_BYTES;        // A_hi | A_lo | B_hi | B_lo = 16 KiB
+constexpr int TC3_SMEM_BYTES = TC3_STAGES * TC3_STAGE_BYTES + 4 * TC2_PATCH_BYTES + 1024;
+constexpr int TC3_TMEM_COLS = 128;
+
+__global__ void __launch_bounds__(192, 2)
+trailing_tf32x3_tile_kernel(float *__restrict__ W, long long ld, int row_skip, int col_skip, int col_skip_n,
+                            const float *__restrict__ imgA, const float *__restrict__ imgB) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_full[TC3_STAGES], bar_empty[TC3_STAGES], bar_done;
+    __shared__ unsigned tmem_slot;
+
+    int tj = blockIdx.x, ti = blockIdx.y;
+    if (col_skip >= 0 && tj >= col_skip) tj += col_skip_n;
+    ti += (ti >= row_skip);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned ring = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+    const unsigned sStage = ring + TC3_STAGES * TC3_STAGE_BYTES;
+    constexpr int NSTEP = 128 / TC3_BK;  // 16 stages per tile
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TC3_STAGES; s++) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(&bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"((unsigned)TC3_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *reinterpret_cast<volatile unsigned *>(&tmem_slot);
+
+    if (warp == 1) {
+        if (lane == 0) {
+            // image of a tile: [k/16][hi|lo][2048 floats]; the two K slices of step kq sit at (kq & 1) * 1024 floats of their chunk
+            const float *ga = imgA + (long long)ti * TC_TILE_IMG_FLOATS;
+            const float *gb = imgB + (long long)tj * TC_TILE_IMG_FLOATS;
+            for (int kq = 0; kq < NSTEP; kq++) {
+                const int s = kq % TC3_STAGES;
+                if (kq >= TC3_STAGES) mbar_wait(&bar_empty[s], (unsigned)((kq / TC3_STAGES) - 1) & 1u);
+                mbar_expect_tx(&bar_full[s], TC3_STAGE_BYTES);
+                const unsigned dst = ring + (unsigned)s * TC3_STAGE_BYTES;
+                const long long hi = (long long)(kq >> 1) * 2 * TC_CHUNK_FLOATS + (kq & 1) * 1024, lo = hi + TC_CHUNK_FLOATS;
+                bulk_g2s(dst, ga + hi, TC3_PART_BYTES, &bar_full[s]);
+                bulk_g2s(dst + TC3_PART_BYTES, ga + lo, TC3_PART_BYTES, &bar_full[s]);
+                bulk_g2s(dst + 2 * TC3_PART_BYTES, gb + hi, TC3_PART_BYTES, &bar_full[s]);
+                bulk_g2s(dst + 3 * TC3_PART_BYTES, gb + lo, TC3_PART_BYTES, &bar_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 0) {
+        if (lane == 0) {
+            for (int kq = 0; kq < NSTEP; kq++) {
+                const int s = kq % TC3_STAGES;
+                mbar_wait(&bar_full[s], (unsigned)(kq / TC3_STAGES) & 1u);
+                tc_fence_after();
+                const unsigned base = ring + (unsigned)s * TC3_STAGE_BYTES;
+                const unsigned long long a_hi = tc_desc(base), a_lo = tc_desc(base + TC3_PART_BYTES);
+                const unsigned long long b_hi = tc_desc(base + 2 * TC3_PART_BYTES), b_lo = tc_desc(base + 3 * TC3_PART_BYTES);
+                tc_mma_tf32(tmem, a_lo, b_hi, TC_IDESC, kq != 0);
+                tc_mma_tf32(tmem, a_hi, b_lo, TC_IDESC, 1u);
+                tc_mma_tf32(tmem, a_hi, b_hi, TC_IDESC, 1u);
+                tc_commit(&bar_empty[s]);
+            }
+            tc_commit(&bar_done);
+        }
+        __syncwarp();
+    } else {
+        // epilogue as in the strip kernel (TMEM -> padded patch -> 4 rows x 128 B per instruction); the register budget at
+        // two CTAs per SM holds half a tile of W, so chunks 2 and 3 are fetched into the registers of chunks 0 and 1
+        const int q = warp & 3, ew = warp - 2;
+        const int rsub = lane >> 3, csub = (lane & 7) * 4;
+        const unsigned stage = sStage + (unsigned)ew * TC2_PATCH_BYTES;
+        float *wt = W + ((long long)ti * TC_TILE + q * 32 + rsub) * ld + csub + (long long)tj * TC_TILE;
+        float4 c[16];
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) c[ch * 8 + i] = *reinterpret_cast<const float4 *>(wt + (long long)(4 * i) * ld + 32 * ch);
+        mbar_wait(&bar_done, 0);
+        tc_fence_after();
+        const unsigned taddr = tmem + ((unsigned)(q * 32) << 16);
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            unsigned d[32];
+            tmem_ld32(taddr + (unsigned)(32 * ch), d);
+            tmem_ld_wait();
+#pragma unroll
+            for (int v = 0; v < 8; v++)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (unsigned)lane * TC2_STAGE_ROW_BYTES + 16u * v),
+                             "r"(d[4 * v]), "r"(d[4 * v + 1]), "r"(d[4 * v + 2]), "r"(d[4 * v + 3])
+                             : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float4 dd;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(dd.x), "=f"(dd.y), "=f"(dd.z), "=f"(dd.w)
+                             : "r"(stage + (unsigned)(4 * i + rsub) * TC2_STAGE_ROW_BYTES + 4u * csub)
+                             : "memory");
+                const float4 cc = c[(ch & 1) * 8 + i];
+                *reinterpret_cast<float4 *>(wt + (long long)(4 * i) * ld + 32 * ch) =
+                    make_float4(cc.x - dd.x, cc.y - dd.y, cc.z - dd.z, cc.w - dd.w);
+            }
+            if (ch < 2) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) c[ch * 8 + i] = *reinterpret_cast<const float4 *>(wt + (long long)(4 * i) * ld + 32 * (ch + 2));
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)TC3_TMEM_COLS) : "memory");
+    }
+}
+
 }  // namespace
 
 size_t tf32x3_image_bytes(int tiles) { return (size_t)tiles * TC_TILE_IMG_FLOATS * sizeof(float); }
@@ -360,6 +496,16 @@ static int tc_strip_len(int gx, int gy) {
     return best;
 }
 
+// MATINV_TC_KERNEL=tile selects the experimental one-tile-per-CTA kernel (default: the strip kernel)
+static bool tc_tile_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MATINV_TC_KERNEL");
+        v = (e && e[0] == 't') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 // Same tile selection as launch_trailing_gemm_ex (gj_gemm.cu).  imgA must hold nrow_tiles tile images, imgB ncol_tiles; both are
 // scratch owned by the caller and must not be shared with a launch that may run concurrently on another stream.
 cudaError_t launch_trailing_tf32x3(float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n,
@@ -374,6 +520,15 @@ cudaError_t launch_trailing_tf32x3(float *W, long long ld, int nrow_tiles, int n
     const int gx = ncol_tiles - (col_skip >= 0 ? col_skip_n : 0), gy = nrow_tiles - 1;
     if (gx <= 0 || gy <= 0) return cudaSuccess;
     tf32_split_kernel<<<nrow_tiles + ncol_tiles, 256, 0, st>>>(CmT, ldc, imgA, nrow_tiles, U, ldu, imgB, kb);
+    if (tc_tile_variant()) {  // experimental, off by default
+        static bool configured_tile[64] = {};
+        if (first_use_on_device(configured_tile)) {
+            cudaError_t e = cudaFuncSetAttribute(trailing_tf32x3_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+        }
+        trailing_tf32x3_tile_kernel<<<dim3(gx, gy), 192, TC3_SMEM_BYTES, st>>>(W, ld, row_skip, col_skip, col_skip_n, imgA, imgB);
+        return cudaGetLastError();
+    }
     const int L = tc_strip_len(gx, gy);
     // <2, 3> (a second epilogue warp-group, one per accumulator) was measured slower: 0.607 vs 0.550 ms per update at N=16384
     // (320 threads cap the epilogue at 168 registers and spill)
