@@ -27,9 +27,10 @@
 // What bounds it: 2 x 64 KiB of W traffic per tile against 3 x 2 x 128^3 tensor flops -- a streaming pass over the 2.1 GB
 // of W touched by one trailing update at N=16384 would take 0.33 ms at the measured 6.4 TB/s, the 3xTF32 MMAs 0.18 ms at the
 // nominal TF32 peak; the FP32 SIMT kernel is FP32-pipe-bound at 1.19 ms.  Measured: 0.55 ms = 3.85 TB/s of W traffic.  The
-// gap to 0.33 ms is the access pattern, not the pipeline: a pure read-modify-write of W in 128 x 128 tiles (512-byte row
-// segments 64 KiB apart) tops out at 0.455-0.49 ms (tools/tile_rmw_probe.cu: 4.4-4.7 TB/s against 6.24 linear), and neither a
-// deeper operand pipeline (the tile kernel below) nor prefetching W a tile ahead moved the number.
+// gap to 0.33 ms is the structure of the W traffic, not the MMA pipeline: a pure read-modify-write of W in 128 x 128 tiles
+// carried in registers tops out at 0.49 ms at one CTA per SM (tools/tile_rmw_probe.cu; 0.345 ms linear; a panel-major W changes
+// little; 128 x 256 tiles at two CTAs per SM, 256 KiB in flight and out of phase, reach 0.322 ms), and neither a deeper operand
+// pipeline (the tile kernel below) nor prefetching W a tile ahead moved the number.
 // History on B200: one tile per CTA with both operands re-read per tile and a row-per-lane epilogue 0.92 ms; resident A +
 // double-buffered accumulator 0.76 ms; coalesced epilogue 0.55 ms.
 #include <stdlib.h>

@@ -38,6 +38,43 @@ __global__ void __launch_bounds__(TW, 1) tile_rmw(float *w, long long ld) {
         }
 }
 
+// The same 128 x 128 tile when W is stored PANEL-MAJOR (W[tj][i][jj]: every tile column an n x 128 row-major matrix, so a
+// tile is 64 KiB contiguous and the panel kernels keep their (pointer, ld = 128) addressing): what a layout change buys.
+__global__ void __launch_bounds__(128, 1) tile_rmw_panel_major(float *w, int n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *base = w + (long long)blockIdx.x * n * 128 + ((long long)blockIdx.y * 128 + warp * 32 + (lane >> 3)) * 128 + (lane & 7) * 4;
+    float4 c[32];
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) c[ch * 8 + i] = *reinterpret_cast<const float4 *>(base + (4 * i) * 128 + 32 * ch);
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float4 v = c[ch * 8 + i];
+            v.x -= 1.f; v.y -= 1.f; v.z -= 1.f; v.w -= 1.f;
+            *reinterpret_cast<float4 *>(base + (4 * i) * 128 + 32 * ch) = v;
+        }
+}
+
+static float time_panel_major(float *w, int n, int reps, int occ) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    dim3 grid(n / 128, n / 128);
+    const int smem = 220 * 1024 / occ - 2048;
+    cudaFuncSetAttribute(tile_rmw_panel_major, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    tile_rmw_panel_major<<<grid, 128, smem>>>(w, n);
+    cudaEventRecord(e0);
+    for (int r = 0; r < reps; r++) tile_rmw_panel_major<<<grid, 128, smem>>>(w, n);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    return ms / reps;
+}
+
 // occ = CTAs per SM, enforced through an unused dynamic shared-memory request (the depth of loads in flight per SM is
 // occ x TW/128 x 64 KiB; the tcgen05 strip kernel has 64 KiB, the tile kernel 2 x 32 KiB)
 template <int TW>
@@ -87,6 +124,18 @@ int main(int argc, char **argv) {
     {
         const float t = time_tile<512>(w, n, reps, 1);
         printf("n=%d  tiles 128 x 512  (2 KiB per row), 1 CTA/SM (256 KiB in flight): %.3f ms  %.2f TB/s\n", n, t, bytes / (t * 1e-3) / 1e12);
+    }
+    for (int occ = 1; occ <= 3; occ++) {
+        const float t = time_panel_major(w, n, reps, occ);
+        printf("n=%d  tiles 128 x 128 of a PANEL-MAJOR W (64 KiB contiguous), %d CTA/SM: %.3f ms  %.2f TB/s\n", n, occ, t, bytes / (t * 1e-3) / 1e12);
+    }
+    for (int occ : occs) {  // the first rows again, to see how repeatable the numbers are
+        const float t = time_tile<128>(w, n, reps, occ);
+        printf("n=%d  (again) tiles 128 x 128, %d CTA/SM: %.3f ms  %.2f TB/s\n", n, occ, t, bytes / (t * 1e-3) / 1e12);
+    }
+    {
+        const float t = time_tile<256>(w, n, reps, 2);
+        printf("n=%d  (again) tiles 128 x 256, 2 CTA/SM: %.3f ms  %.2f TB/s\n", n, t, bytes / (t * 1e-3) / 1e12);
     }
     cudaError_t e = cudaDeviceSynchronize();
     printf("%s\n", e == cudaSuccess ? "done" : cudaGetErrorString(e));
