@@ -307,13 +307,18 @@ def main():
         tc_ms = prof_tc["gemm_ms"] / max(prof_tc["gemm_launches"], 1)
         tc_bytes = prof_tc["gemm_flops"] / max(prof_tc["gemm_launches"], 1) / 32.0   # 8 B (read + write) per 2*128 flops
         tc_gbs = tc_bytes / (tc_ms * 1e-3) / 1e9 if tc_ms else 0.0
+        tc_traffic = None
+        ttf = ROOT / "profiles" / "r01_tf32x3_traffic.json"
+        if n == 16384 and ttf.exists():   # DRAM bytes of one strip-kernel launch, from the committed ncu --set full capture
+            tc_traffic = json.loads(ttf.read_text())["dram_bytes_total"]
         extra["tf32x3"] = {
             "value": world * flops / (ms_tc * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_tc,
             "speedup_vs_fp32_simt": ms / ms_tc, "residual_estimate": st_tc["estimate"], "fell_back": st_tc["fell_back"],
             "residual": m.residual_dev(A, X)[0] if n <= 16384 else None, "gate": m.TF32X3_GATE,
             "gpu_launches": prof_tc["launches"],
             "roofline": {"bound": "hbm", "kernel": "tf32_split_kernel + trailing_tf32x3_strip_kernel (tcgen05.mma kind::tf32, TMEM)",
-                         "achieved": tc_gbs, "peak": hbm, "unit": "GB/s", "frac": tc_gbs / hbm, "traffic": None,
+                         "achieved": tc_gbs, "peak": hbm, "unit": "GB/s", "frac": tc_gbs / hbm, "traffic": tc_traffic,
+                         "traffic_note": "DRAM bytes per launch (ncu, profiles/r01_tf32x3_traffic.json)",
                          "algorithmic_bytes_per_launch": tc_bytes, "ms_per_launch": tc_ms,
                          "tensor_tflops_3x": 3.0 * prof_tc["gemm_flops"] / max(prof_tc["gemm_launches"], 1) / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
