@@ -56,10 +56,14 @@ __device__ __forceinline__ void bulk_s2g(void *dst, unsigned src_smem, unsigned 
 }
 
 constexpr int TILE = 128;
-constexpr int SLOT_BYTES = TILE * TILE * 4;  // 64 KiB, rows packed (512 B each)
-
-template <int DEPTH>
+// PADDED = 0: slot rows packed (512 B), consumers walk the slot linearly.
+// PADDED = 1: slot rows 528 B apart and every consumer thread owns one ROW (lane = row, like the TMEM accumulator layout):
+//             the access pattern of an epilogue that subtracts tcgen05.ld data in place, with no transpose; the 16-byte
+//             pad makes the 8 lanes of a quarter-warp hit distinct 16-byte bank groups.
+template <int DEPTH, int PADDED>
 __global__ void __launch_bounds__(160, 1) tile_rmw_tma(float *w, long long ld, int tiles_x, int ntiles) {
+    constexpr unsigned ROW = PADDED ? 528u : 512u;
+    constexpr int SLOT_BYTES = TILE * (int)ROW;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar_full[DEPTH], bar_empty[DEPTH];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -79,9 +83,9 @@ __global__ void __launch_bounds__(160, 1) tile_rmw_tma(float *w, long long ld, i
                 const int t = blockIdx.x + it * gridDim.x, s = it % DEPTH;
                 if (it >= DEPTH) mbar_wait(&bar_empty[s], (unsigned)((it / DEPTH) - 1) & 1u);
                 float *tile = w + (long long)(t / tiles_x) * TILE * ld + (long long)(t % tiles_x) * TILE;
-                mbar_expect_tx(&bar_full[s], SLOT_BYTES);
+                mbar_expect_tx(&bar_full[s], TILE * 512u);
                 for (int r = 0; r < TILE; r++)
-                    bulk_g2s(slots + (unsigned)s * SLOT_BYTES + (unsigned)r * 512u, tile + (long long)r * ld, 512u, &bar_full[s]);
+                    bulk_g2s(slots + (unsigned)s * SLOT_BYTES + (unsigned)r * ROW, tile + (long long)r * ld, 512u, &bar_full[s]);
             }
         }
         __syncwarp();
@@ -91,17 +95,27 @@ __global__ void __launch_bounds__(160, 1) tile_rmw_tma(float *w, long long ld, i
             const int t = blockIdx.x + it * gridDim.x, s = it % DEPTH;
             mbar_wait(&bar_full[s], (unsigned)(it / DEPTH) & 1u);
             float4 *slot = reinterpret_cast<float4 *>(smem + (size_t)s * SLOT_BYTES);
+            if (PADDED) {
+                float4 *row = slot + (size_t)ct * (ROW / 16);  // thread = row
 #pragma unroll 8
-            for (int e = ct; e < SLOT_BYTES / 16; e += 128) {  // consecutive threads, consecutive 16 B: conflict-free
-                float4 v = slot[e];
-                v.x -= 1.f; v.y -= 1.f; v.z -= 1.f; v.w -= 1.f;
-                slot[e] = v;
+                for (int c = 0; c < 32; c++) {
+                    float4 v = row[c];
+                    v.x -= 1.f; v.y -= 1.f; v.z -= 1.f; v.w -= 1.f;
+                    row[c] = v;
+                }
+            } else {
+#pragma unroll 8
+                for (int e = ct; e < SLOT_BYTES / 16; e += 128) {  // consecutive threads, consecutive 16 B: conflict-free
+                    float4 v = slot[e];
+                    v.x -= 1.f; v.y -= 1.f; v.z -= 1.f; v.w -= 1.f;
+                    slot[e] = v;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the bulk store
             asm volatile("bar.sync 1, 128;" ::: "memory");                // the four consumer warps only
             if (ct == 0) {
                 float *tile = w + (long long)(t / tiles_x) * TILE * ld + (long long)(t % tiles_x) * TILE;
-                for (int r = 0; r < TILE; r++) bulk_s2g(tile + (long long)r * ld, slots + (unsigned)s * SLOT_BYTES + (unsigned)r * 512u, 512u);
+                for (int r = 0; r < TILE; r++) bulk_s2g(tile + (long long)r * ld, slots + (unsigned)s * SLOT_BYTES + (unsigned)r * ROW, 512u);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slot has been read: it may be refilled
                 mbar_arrive(&bar_empty[s]);
@@ -111,28 +125,29 @@ __global__ void __launch_bounds__(160, 1) tile_rmw_tma(float *w, long long ld, i
     }
 }
 
-template <int DEPTH>
+template <int DEPTH, int PADDED>
 static void run(float *w, int n, int reps, int *passes) {
+    constexpr int SLOT_BYTES = TILE * (PADDED ? 528 : 512);
     const int tiles_x = n / TILE, ntiles = tiles_x * tiles_x;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     // one CTA per SM even at DEPTH = 1: pad the request so that two CTAs never fit
     const int smem = DEPTH * SLOT_BYTES > 120 * 1024 ? DEPTH * SLOT_BYTES : 120 * 1024;
-    cudaFuncSetAttribute(tile_rmw_tma<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(tile_rmw_tma<DEPTH, PADDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    tile_rmw_tma<DEPTH><<<sms, 160, smem>>>(w, n, tiles_x, ntiles);
+    tile_rmw_tma<DEPTH, PADDED><<<sms, 160, smem>>>(w, n, tiles_x, ntiles);
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; r++) tile_rmw_tma<DEPTH><<<sms, 160, smem>>>(w, n, tiles_x, ntiles);
+    for (int r = 0; r < reps; r++) tile_rmw_tma<DEPTH, PADDED><<<sms, 160, smem>>>(w, n, tiles_x, ntiles);
     cudaEventRecord(e1);
     const cudaError_t e = cudaEventSynchronize(e1);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     *passes += reps + 1;
     const double bytes = 2.0 * n * (double)n * 4;
-    printf("n=%d  TMA-staged 128 x 128 tiles, 1 CTA/SM, %d deep (%3d KiB of smem): %.3f ms  %.2f TB/s   %s\n", n, DEPTH,
-           DEPTH * 64, ms / reps, bytes / (ms / reps * 1e-3) / 1e12, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    printf("n=%d  TMA-staged 128 x 128 tiles, 1 CTA/SM, %d deep (%3d KiB of smem), %s: %.3f ms  %.2f TB/s   %s\n", n, DEPTH,
+           DEPTH * SLOT_BYTES / 1024, PADDED ? "padded rows, thread = row" : "packed rows, linear walk  ", ms / reps, bytes / (ms / reps * 1e-3) / 1e12, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
 int main(int argc, char **argv) {
@@ -141,9 +156,12 @@ int main(int argc, char **argv) {
     if (n % TILE || cudaMalloc(&w, (size_t)n * n * 4) != cudaSuccess) { printf("bad n / alloc failed\n"); return 1; }
     cudaMemset(w, 0, (size_t)n * n * 4);
     int passes = 0;
-    run<1>(w, n, reps, &passes);
-    run<2>(w, n, reps, &passes);
-    run<3>(w, n, reps, &passes);
+    run<1, 0>(w, n, reps, &passes);
+    run<2, 0>(w, n, reps, &passes);
+    run<3, 0>(w, n, reps, &passes);
+    run<1, 1>(w, n, reps, &passes);
+    run<2, 1>(w, n, reps, &passes);
+    run<3, 1>(w, n, reps, &passes);
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("FAIL: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
     // self-check on a sample of rows: every element was decremented exactly `passes` times
     std::vector<float> row(n);
