@@ -21,12 +21,13 @@ import numpy as np
 
 __all__ = ["lib", "matrix_inv_32", "invert", "invert_dev", "invert_batched", "invert_batched_dev", "device_count",
            "last_error", "last_timing", "MatinvError", "OK", "SINGULAR", "FLAG_UNBLOCKED", "FLAG_VERBOSE",
-           "FLAG_NOCHECK", "FLAG_TF32X3", "TF32X3_GATE", "tf32x3_status", "debug_trailing_update", "probe_residual_dev", "EXPORTS"]
+           "FLAG_NOCHECK", "FLAG_TF32X3", "TF32X3_GATE", "tf32x3_status", "debug_trailing_update", "probe_residual_dev", "tf32x3_gate_dev", "TF32X3_GATE_SCALED", "EXPORTS"]
 
 OK, SINGULAR = 0, 1
 E_INVALID, E_NODEVICE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
 FLAG_TF32X3, FLAG_UNBLOCKED, FLAG_VERBOSE, FLAG_NOCHECK, FLAG_NOPIVOT = 1, 2, 4, 8, 16
 TF32X3_GATE = 1e-5   # MATINV_TF32X3_GATE (include/matinv_shim.h)
+TF32X3_GATE_SCALED = 1e-7   # MATINV_TF32X3_GATE_SCALED: bound on estimate * sqrt(n)
 
 _SO = Path(__file__).resolve().parent / "libmatinv32.so"
 
@@ -39,7 +40,7 @@ EXPORTS = [
     "matinv_shard_apply", "matinv_shard_apply_ex", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
     "matinv_profile_read", "matinv_debug_trace", "matinv_invert_f64", "matinv_invert_f64_dev", "matinv_residual_f64_dev",
-    "matinv_host_defect_f64", "matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev",
+    "matinv_host_defect_f64", "matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev", "matinv_tf32x3_gate_dev",
 ]
 
 
@@ -99,7 +100,8 @@ def _load() -> ctypes.CDLL:
     L.matinv_tf32x3_status.argtypes = [dp, ip, ctypes.POINTER(ll), ctypes.POINTER(ll)]
     L.matinv_debug_trailing_update.argtypes = [fp, ll, i, i, fp, fp, i, i, dp, vp]
     L.matinv_probe_residual_f32_dev.argtypes = [fp, fp, i, dp, vp]
-    for name in ("matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev"):
+    L.matinv_tf32x3_gate_dev.argtypes = [fp, fp, i, dp, vp]
+    for name in ("matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev", "matinv_tf32x3_gate_dev"):
         getattr(L, name).restype = i
     for name in ("matinv_invert_f32", "matinv_invert_f32_dev", "matinv_invert_batched_f32",
                  "matinv_invert_batched_f32_dev", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
@@ -338,6 +340,18 @@ def probe_residual_dev(A, X):
         _check(lib.matinv_probe_residual_f32_dev(_torch_ptr(A), _torch_ptr(X), n, out, ctypes.c_void_p(st)))
     r2, a2, x2 = out[0], out[1], out[2]
     return float(np.sqrt(r2) / (n * np.sqrt(a2) * np.sqrt(x2)))
+
+
+def tf32x3_gate_dev(A, X):
+    """The acceptance rule of FLAG_TF32X3 applied to a given pair of CUDA tensors: (accepted, estimate, estimate * sqrt(n))."""
+    import torch
+
+    n = A.shape[0]
+    out = (ctypes.c_double * 2)()
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    with torch.cuda.device(A.device):
+        rc = _check(lib.matinv_tf32x3_gate_dev(_torch_ptr(A), _torch_ptr(X), n, out, ctypes.c_void_p(st)))
+    return bool(rc), out[0], out[1]
 
 
 def tf32x3_status():

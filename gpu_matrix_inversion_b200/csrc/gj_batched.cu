@@ -433,8 +433,8 @@ static cudaError_t launch_batched_reg(const float *A, long long batch, float *X,
 }
 
 // MATINV_BATCHED: 0 = shared-memory kernel (v0), 1 = one warp per matrix, scalar FMAs (v1), 2 = two warps per matrix (v2),
-// 3 = one warp per matrix on packed pairs, gj_batched_pk.cu (v3, default: 2.50e7 inversions/s on B200 against 2.19e7 for
-// v1 and 1.7e7 for v2)
+// 3 = one warp per matrix on packed pairs, gj_batched_pk.cu (v3, default: 2.50e7 inversions/s on B200 against 2.19e7 for v1 and
+// 1.7e7 for v2), 4 = v3's layout blocked in 8-column panels with look-ahead, gj_batched_blk.cu (v4: same rate, see its header)
 static int batched_mode() {
     static int mode = -1;
     if (mode < 0) {
@@ -446,7 +446,8 @@ static int batched_mode() {
 
 cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st) {
     if (batched_mode() >= 1) {
-        if ((n == 64 || n == 32) && batched_mode() >= 3) return launch_batched_pk(A, n, batch, X, info, st);
+        if ((n == 64 || n == 32) && batched_mode() >= 4) return launch_batched_blk(A, n, batch, X, info, st);
+        if ((n == 64 || n == 32) && batched_mode() == 3) return launch_batched_pk(A, n, batch, X, info, st);
         if (n == 64 && batched_mode() == 2) return launch_batched_row64(A, batch, X, info, st);
         if (n == 64) return launch_batched_reg<64>(A, batch, X, info, st);
         if (n == 32) return launch_batched_reg<32>(A, batch, X, info, st);

@@ -112,7 +112,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
             : "r"(a), "r"(parity)
             : "memory");
         if (ok) return;
-        if ((spins & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();  // ~2 s
+        // ~20 s at 2 GHz: far beyond any legitimate wait (a whole inversion takes 0.1-1 s) yet bounded; long enough not to fire
+        // under compute-sanitizer, a debugger or time-slicing with another process
+        if ((spins & 1023u) == 1023u && clock64() - t0 > 40000000000ll) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {

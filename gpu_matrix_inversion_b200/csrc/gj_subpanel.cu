@@ -20,6 +20,9 @@
 //
 // The panel ping-pongs between two buffers per sub-panel (like the reference's two [A|I] buffers,
 // :352-359), so the update kernel never reads a row another CTA has already rewritten.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -551,7 +554,34 @@ static cudaError_t launch_subpanel_t(int ncta, const float *in, long long ld_in,
 static int g_panel_critical = 0;
 void panel_set_critical(int on) { g_panel_critical = on; }
 
-int subpanel_width(int n) { return (n > 32768) ? 8 : 16; }
+// MATINV_SUBPANEL_SHAPE = WxRxTH forces one instantiation of the sub-panel kernel for every n it can hold (16 CTAs x TH
+// threads x R rows), so that the shapes the large orders select -- 16x4x512 for 16384 < n <= 32768, 8x8x512 (8-wide
+// sub-panels) above -- can be checked bit for bit against the oracle at orders the oracle finishes in seconds
+// (tests/test_gpu_parity.py::test_subpanel_shapes_bit_identical).  Read once per process; 0 = not forced.
+static int forced_shape() {
+    static int shape = -1;
+    if (shape < 0) {
+        const char *e = getenv("MATINV_SUBPANEL_SHAPE");
+        shape = 0;
+        if (e && e[0]) {
+            int w = 0, r = 0, th = 0;
+            if (sscanf(e, "%dx%dx%d", &w, &r, &th) == 3) {
+                if (w == 16 && r == 2 && th == 512) shape = 1;
+                else if (w == 16 && r == 4 && th == 256) shape = 2;
+                else if (w == 16 && r == 4 && th == 512) shape = 3;
+                else if (w == 8 && r == 8 && th == 512) shape = 4;
+            }
+        }
+    }
+    return shape;
+}
+static int forced_capacity(int shape) { return shape == 1 ? 16384 : shape == 2 ? 16384 : shape == 3 ? 32768 : shape == 4 ? 65536 : 0; }
+
+int subpanel_width(int n) {
+    const int f = forced_shape();
+    if (f && n <= forced_capacity(f)) return f == 4 ? 8 : 16;
+    return (n > 32768) ? 8 : 16;
+}
 bool subpanel_supported(int n) { return n <= 65536; }
 
 // Rows per cluster = ncta x TH x R.  512-thread CTAs with 2 rows per thread measured fastest at N=16384 on B200
@@ -559,6 +589,12 @@ bool subpanel_supported(int n) { return n <= 65536; }
 cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long long ld_out, int n, int k0, int s0,
                             int sw, float *CmT, long long ldc, int *piv, float *pv, int *info, cudaStream_t st) {
 #define SP_ARGS in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st
+    if (const int f = forced_shape(); f && n <= forced_capacity(f)) {
+        if (f == 1) return launch_subpanel_t<16, 2, 512>(16, SP_ARGS);
+        if (f == 2) return launch_subpanel_t<16, 4, 256>(16, SP_ARGS);
+        if (f == 3) return launch_subpanel_t<16, 4, 512>(16, SP_ARGS);
+        return launch_subpanel_t<8, 8, 512>(16, SP_ARGS);
+    }
     if (n <= 8192) {
         int ncta = 1;
         while (ncta * 512 < n) ncta *= 2;

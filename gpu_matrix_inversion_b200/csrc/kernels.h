@@ -85,6 +85,7 @@ void launch_load(const float *A, int n, float *W, long long ld, int npad, cudaSt
 // ---- gj_batched.cu : n <= 128, one CTA per matrix
 cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st);
 cudaError_t launch_batched_pk(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st);
+cudaError_t launch_batched_blk(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st);
 
 // ---- generate.cu : synthetic workloads, residual, FFMA peak
 void launch_generate(float *A, int n, long long ld, u64 seed, int kind, int col0, int ncols, cudaStream_t st);

@@ -48,13 +48,26 @@ int fail(int code, const char *fmt, ...) {
 struct Profile {
     bool on = false;
     long long launches = 0;
-    std::vector<cudaEvent_t> ev;  // pairs
+    std::vector<cudaEvent_t> ev;  // pairs; all created on device `dev`
+    int dev = -1;
     size_t used = 0;
     double gemm_flops = 0.0;
 } g_prof;
 #define COUNT_LAUNCH(k) (g_prof.launches += (k))
 
 cudaEvent_t prof_event() {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (g_prof.dev != cur) {   // events belong to one device: start over when the caller has moved to another one
+        if (g_prof.dev >= 0 && !g_prof.ev.empty()) {
+            cudaSetDevice(g_prof.dev);
+            for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+            cudaSetDevice(cur);
+        }
+        g_prof.ev.clear();
+        g_prof.used = 0;
+        g_prof.dev = cur;
+    }
     if (g_prof.used == g_prof.ev.size()) {
         cudaEvent_t e;
         cudaEventCreate(&e);
@@ -83,11 +96,9 @@ struct Workspace {
     int tc_npad = 0;
 };
 
-struct Context {
-    std::mutex mu;
-    bool probed = false;
-    int ndev = 0;
-    int device = -1;  // device the cached workspace / streams live on
+// Everything cached between calls belongs to exactly one device; one cache per device so that callers (or threads)
+// working on different GPUs of one process do not evict each other's workspaces.
+struct DeviceCache {
     Workspace ws;
     F64Workspace wsd;                     // FP64 path (gj_f64.cu)
     cudaStream_t stream = nullptr;
@@ -102,12 +113,23 @@ struct Context {
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     cudaStream_t panel_stream = nullptr;  // high priority: the latency-critical panel kernels
     cudaEvent_t ev_a = nullptr, ev_p = nullptr;
+    bool used = false;
+};
+
+constexpr int MAX_DEVICES = 64;
+
+struct Context {
+    std::mutex mu;
+    bool probed = false;
+    int ndev = 0;
+    int cur = 0;              // device of the call in progress (set by probe_locked under mu)
+    DeviceCache dc[MAX_DEVICES];
 } g;
+#define G (g.dc[g.cur])
 
 void release_locked();
 
-// Device count; also rebinds the cached workspace and streams when the caller has switched the current
-// device since the last call (everything cached belongs to exactly one device).
+// Device count; also selects the cache of the caller's current device.
 int probe_locked() {
     if (!g.probed) {
         int n = 0;
@@ -118,12 +140,8 @@ int probe_locked() {
     if (g.ndev > 0) {
         int cur = 0;
         cudaGetDevice(&cur);
-        if (g.device >= 0 && g.device != cur) {
-            cudaSetDevice(g.device);
-            release_locked();
-            cudaSetDevice(cur);
-        }
-        g.device = cur;
+        g.cur = (cur >= 0 && cur < MAX_DEVICES) ? cur : 0;
+        G.used = true;
     }
     return g.ndev;
 }
@@ -138,30 +156,30 @@ void free_ws(Workspace &w) {
 }
 
 void release_locked() {
-    free_ws(g.ws);
-    f64_workspace_free(g.wsd);
-    cudaFree(g.hostio); g.hostio = nullptr; g.hostio_bytes = 0;
-    cudaFree(g.hostio_i); g.hostio_i = nullptr; g.hostio_i_bytes = 0;
-    cudaFree(g.hostx); g.hostx = nullptr; g.hostx_bytes = 0;
-    if (g.copy_stream) {
-        cudaEventDestroy(g.ev_chunk[0]); cudaEventDestroy(g.ev_chunk[1]);
-        cudaStreamDestroy(g.copy_stream);
-        g.copy_stream = nullptr;
+    free_ws(G.ws);
+    f64_workspace_free(G.wsd);
+    cudaFree(G.hostio); G.hostio = nullptr; G.hostio_bytes = 0;
+    cudaFree(G.hostio_i); G.hostio_i = nullptr; G.hostio_i_bytes = 0;
+    cudaFree(G.hostx); G.hostx = nullptr; G.hostx_bytes = 0;
+    if (G.copy_stream) {
+        cudaEventDestroy(G.ev_chunk[0]); cudaEventDestroy(G.ev_chunk[1]);
+        cudaStreamDestroy(G.copy_stream);
+        G.copy_stream = nullptr;
     }
-    if (g.panel_stream) {
-        cudaEventDestroy(g.ev_a); cudaEventDestroy(g.ev_p);
-        cudaStreamDestroy(g.panel_stream);
-        g.panel_stream = nullptr;
+    if (G.panel_stream) {
+        cudaEventDestroy(G.ev_a); cudaEventDestroy(G.ev_p);
+        cudaStreamDestroy(G.panel_stream);
+        G.panel_stream = nullptr;
     }
-    if (g.stream) {
-        cudaEventDestroy(g.ev[0]); cudaEventDestroy(g.ev[1]);
-        cudaStreamDestroy(g.stream);
-        g.stream = nullptr;
+    if (G.stream) {
+        cudaEventDestroy(G.ev[0]); cudaEventDestroy(G.ev[1]);
+        cudaStreamDestroy(G.stream);
+        G.stream = nullptr;
     }
 }
 
 int ensure_ws(int npad) {
-    Workspace &w = g.ws;
+    Workspace &w = G.ws;
     if (w.npad == npad) return 0;
     free_ws(w);
     const size_t N = (size_t)npad;
@@ -196,19 +214,19 @@ int ensure_ws(int npad) {
 }
 
 int ensure_copy_stream() {
-    if (!g.copy_stream) {
-        CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&g.ev_chunk[0], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&g.ev_chunk[1], cudaEventDisableTiming));
+    if (!G.copy_stream) {
+        CK(cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&G.ev_chunk[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&G.ev_chunk[1], cudaEventDisableTiming));
     }
     return 0;
 }
 
 int ensure_stream() {
-    if (!g.stream) {
-        CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-        CK(cudaEventCreate(&g.ev[0]));
-        CK(cudaEventCreate(&g.ev[1]));
+    if (!G.stream) {
+        CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&G.ev[0]));
+        CK(cudaEventCreate(&G.ev[1]));
     }
     return 0;
 }
@@ -268,9 +286,26 @@ struct TcState {
     bool on = false;
     bool used = false;            // the last factorisation ran its trailing updates on the tensor cores
     double last_estimate = -1.0;  // residual estimate of the last gated inversion
+    double last_estimate_scaled = -1.0;  // the same times sqrt(n): the size-independent quantity the gate also bounds
     int last_fallback = 0;        // 1 = the gate rejected the 3xTF32 result and the FP32 SIMT schedule was run
     long long inversions = 0, fallbacks = 0;
 } g_tc;
+
+// The gate of MATINV_FLAG_TF32X3.  r = {||A X - I||_F^2 (estimate), ||A||_F^2, ||X||_F^2}.  Two conditions, both false for NaN:
+//   est        = ||AX-I||_F / (n ||A||_F ||X||_F)  <= MATINV_TF32X3_GATE (north_star's 1e-5 tolerance), and
+//   est_scaled = est * sqrt(n)                      <= MATINV_TF32X3_GATE_SCALED.
+// The first alone barely constrains a large matrix: for an X unrelated to inv(A) it is ~ n^-1.5 (5e-6 at n = 2048), so it
+// only rejects NaN and total garbage at the orders where the tensor-core path matters.  est * sqrt(n) does not shrink
+// with n -- the FP32 SIMT path measures 2.6e-9 at n = 1024 and 3.6e-9 at n = 16384 on the uniform workload -- so a fixed
+// bound of 1e-7 (~30x what the bit-exact path achieves) rejects an unrelated inverse (2e-4 at n = 2048) and an inverse
+// with 1 % relative noise (2e-5 at n = 512) at every order; a rejected result is recomputed by the FP32 SIMT schedule.
+bool tf32x3_gate_accepts(const double r[3], int n, double *est_out, double *est_scaled_out) {
+    const double est = sqrt(r[0]) / ((double)n * sqrt(r[1]) * sqrt(r[2]));
+    const double est_scaled = est * sqrt((double)n);
+    if (est_out) *est_out = est;
+    if (est_scaled_out) *est_scaled_out = est_scaled;
+    return est <= MATINV_TF32X3_GATE && est_scaled <= MATINV_TF32X3_GATE_SCALED;
+}
 
 int ensure_tc(Workspace &w) {
     if (w.tc_npad == w.npad) return 0;
@@ -291,11 +326,17 @@ int ensure_tc(Workspace &w) {
     return 0;
 }
 
+// First error reported by a launcher during the schedule in progress (under the context lock).  The schedules only enqueue;
+// once an error is recorded they stop launching the tensor-core kernels and factor_locked fails the call.
+cudaError_t g_sched_err = cudaSuccess;
+
 void trailing_ex(Workspace &w, float *W, long long ld, int nrow_tiles, int ncol_tiles, int row_skip, int col_skip, int col_skip_n,
                  int kb, const float *CmT, long long ldc, const float *U, long long ldu, cudaStream_t st, int side) {
     if (g_tc.on && (side == 0 || ncol_tiles == 1)) {
-        launch_trailing_tf32x3(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu, w.tcA[side],
-                               w.tcB[side], st);
+        if (g_sched_err != cudaSuccess) return;   // a previous launch failed: do not pile dependent work on top of it
+        const cudaError_t e = launch_trailing_tf32x3(W, ld, nrow_tiles, ncol_tiles, row_skip, col_skip, col_skip_n, kb, CmT, ldc, U, ldu,
+                                                     w.tcA[side], w.tcB[side], st);
+        if (e != cudaSuccess) g_sched_err = e;
         COUNT_LAUNCH(1);  // the split kernel; callers count the update itself
         return;
     }
@@ -328,12 +369,12 @@ void schedule_blocked(Workspace &w, int n, cudaStream_t st) {
 // (GEMM_A), then panel k+1 is factored on a high-priority stream WHILE the rest of the trailing update of panel k
 // (GEMM_B) keeps the other SMs busy.  Same kernels, same FMA chains -- only the order of independent work changes.
 int ensure_lookahead() {
-    if (!g.panel_stream) {
+    if (!G.panel_stream) {
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&g.panel_stream, cudaStreamNonBlocking, hi));
-        CK(cudaEventCreateWithFlags(&g.ev_a, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&g.ev_p, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithPriority(&G.panel_stream, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&G.ev_a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&G.ev_p, cudaEventDisableTiming));
     }
     return 0;
 }
@@ -357,7 +398,7 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
     float *CmT[2] = {w.CmT, w.CmT2};
     float *pv[2] = {w.pv, w.pv2};
     PanelState *ps[2] = {w.ps, w.ps2};
-    cudaStream_t sp = g.panel_stream;
+    cudaStream_t sp = G.panel_stream;
     COUNT_LAUNCH(launch_panel_factor(w.W, ld, n, 0, (n < MATINV_NB) ? n : MATINV_NB, CmT[0], ld, w.piv, pv[0], w.info, ps[0],
                                      w.P[0], w.P[1], st));
     for (int k = 0; k < nblk; k++) {
@@ -369,13 +410,13 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
             // The chain needs GEMM_B(k-1) (which updated block k+1) and leaves ev_p for the next iteration.
             const int k1 = k0 + MATINV_NB;
             const int kb1 = (n - k1 < MATINV_NB) ? n - k1 : MATINV_NB;
-            cudaEventRecord(g.ev_a, st);   // everything up to GEMM_B(k-1) (and panel k, joined below / before the loop)
-            cudaStreamWaitEvent(sp, g.ev_a, 0);
+            cudaEventRecord(G.ev_a, st);   // everything up to GEMM_B(k-1) (and panel k, joined below / before the loop)
+            cudaStreamWaitEvent(sp, G.ev_a, 0);
             launch_rowblock_ex(w.W + k1, ld, MATINV_NB, k0, kb, 0, 0, CmT[b], ld, pv[b], ps[b], w.U + k1, ld, sp);
             trailing_ex(w, w.W + k1, ld, nt, 1, k, -1, 0, kb, CmT[b], ld, w.U + k1, ld, sp, 1);
             COUNT_LAUNCH(launch_panel_factor(w.W + k1, ld, n, k1, kb1, CmT[b ^ 1], ld, w.piv, pv[b ^ 1], w.info, ps[b ^ 1], w.P[0],
                                              w.P[1], sp));
-            cudaEventRecord(g.ev_p, sp);
+            cudaEventRecord(G.ev_p, sp);
             launch_rowblock_ex(w.W, ld, w.npad, k0, kb, k, 2, CmT[b], ld, pv[b], ps[b], w.U, ld, st);
             if (g_prof.on) cudaEventRecord(prof_event(), st);
             trailing_ex(w, w.W, ld, nt, nt, k, k, 2, kb, CmT[b], ld, w.U, ld, st, 0);
@@ -384,7 +425,7 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
                 const double m = (double)(w.npad - MATINV_NB);
                 g_prof.gemm_flops += 2.0 * m * (m - MATINV_NB) * kb;   // block k+1 is updated on the other stream
             }
-            cudaStreamWaitEvent(st, g.ev_p, 0);
+            cudaStreamWaitEvent(st, G.ev_p, 0);
             COUNT_LAUNCH(4);
             continue;
         }
@@ -396,14 +437,14 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
             const int kb1 = (n - k1 < MATINV_NB) ? n - k1 : MATINV_NB;
             // GEMM_A: tile column k+1 only
             trailing_ex(w, w.W + k1, ld, nt, 1, k, -1, 0, kb, CmT[b], ld, w.U + k1, ld, st, 1);
-            cudaEventRecord(g.ev_a, st);
-            cudaStreamWaitEvent(sp, g.ev_a, 0);
+            cudaEventRecord(G.ev_a, st);
+            cudaStreamWaitEvent(sp, G.ev_a, 0);
             COUNT_LAUNCH(launch_panel_factor(w.W + k1, ld, n, k1, kb1, CmT[b ^ 1], ld, w.piv, pv[b ^ 1], w.info, ps[b ^ 1], w.P[0],
                                              w.P[1], sp));
-            cudaEventRecord(g.ev_p, sp);
+            cudaEventRecord(G.ev_p, sp);
             // GEMM_B: every other tile column (skips k and k+1)
             trailing_ex(w, w.W, ld, nt, nt, k, k, 2, kb, CmT[b], ld, w.U, ld, st, 0);
-            cudaStreamWaitEvent(st, g.ev_p, 0);
+            cudaStreamWaitEvent(st, G.ev_p, 0);
             COUNT_LAUNCH(2);
         } else {
             trailing_ex(w, w.W, ld, nt, nt, k, k, 1, kb, CmT[b], ld, w.U, ld, st, 0);
@@ -426,7 +467,7 @@ int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags) {
     const int npad = ((n + MATINV_NB - 1) / MATINV_NB) * MATINV_NB;
     int rc = ensure_ws(npad);
     if (rc) return rc;
-    Workspace &w = g.ws;
+    Workspace &w = G.ws;
     g_tc.on = g_tc.used = false;
     if ((flags & MATINV_FLAG_TF32X3) && !(flags & MATINV_FLAG_UNBLOCKED) && npad > MATINV_NB) {
         rc = ensure_tc(w);
@@ -434,6 +475,7 @@ int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags) {
         g_tc.on = g_tc.used = true;
         panel_set_critical(1);
     }
+    g_sched_err = cudaSuccess;
     CK(cudaMemsetAsync(w.info, 0, sizeof(int), st));
     launch_load(A_dev, n, w.W, npad, npad, st);
     if (flags & MATINV_FLAG_UNBLOCKED) schedule_unblocked(w, n, st);
@@ -444,6 +486,10 @@ int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags) {
     } else schedule_blocked(w, n, st);
     g_tc.on = false;
     panel_set_critical(0);
+    if (g_sched_err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MATINV_E_CUDA, "trailing update launch failed: %s", cudaGetErrorString(g_sched_err));
+    }
     COUNT_LAUNCH(3);
     launch_colperm_build(w.piv, n, w.colsrc, st);
     CK(cudaGetLastError());
@@ -452,7 +498,7 @@ int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags) {
 
 int status_locked(cudaStream_t st) {
     int info = 0;
-    CK(cudaMemcpyAsync(&info, g.ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&info, G.ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (info != 0) {
         if (info > 0) snprintf(g_err, sizeof(g_err), "singular: zero or non-finite pivot at column %d", info - 1);
@@ -465,7 +511,7 @@ int status_locked(cudaStream_t st) {
 int invert_dev_once(const float *A_dev, int n, float *X_dev, int *piv_dev, cudaStream_t st, int flags) {
     int rc = factor_locked(A_dev, n, st, flags);
     if (rc) return rc;
-    Workspace &w = g.ws;
+    Workspace &w = G.ws;
     launch_extract(w.W, w.npad, n, w.colsrc, X_dev, w.info, !(flags & MATINV_FLAG_NOCHECK), st);
     if (piv_dev) CK(cudaMemcpyAsync(piv_dev, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
@@ -488,11 +534,13 @@ int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cud
         if (rc == MATINV_OK) {
             if (flags & MATINV_FLAG_NOCHECK) return rc;  // caller opted out of every check (timing runs)
             double r[3] = {0, 0, 0};
-            CK(run_probe_residual(A_dev, X_dev, n, g.ws.probe, r, st));
+            CK(run_probe_residual(A_dev, X_dev, n, G.ws.probe, r, st));
             COUNT_LAUNCH(2);
-            const double est = sqrt(r[0]) / ((double)n * sqrt(r[1]) * sqrt(r[2]));
+            double est = 0.0, est_scaled = 0.0;
+            const bool ok = tf32x3_gate_accepts(r, n, &est, &est_scaled);
             g_tc.last_estimate = est;
-            if (est <= MATINV_TF32X3_GATE) return MATINV_OK;  // false for NaN
+            g_tc.last_estimate_scaled = est_scaled;
+            if (ok) return MATINV_OK;
         }
         g_tc.last_fallback = 1;
         g_tc.fallbacks++;
@@ -502,17 +550,17 @@ int invert_dev_locked(const float *A_dev, int n, float *X_dev, int *piv_dev, cud
 }
 
 int ensure_hostio(size_t bytes, size_t ibytes) {
-    if (g.hostio_bytes < bytes) {
-        cudaFree(g.hostio);
-        g.hostio = nullptr; g.hostio_bytes = 0;
-        CK(cudaMalloc(&g.hostio, bytes));
-        g.hostio_bytes = bytes;
+    if (G.hostio_bytes < bytes) {
+        cudaFree(G.hostio);
+        G.hostio = nullptr; G.hostio_bytes = 0;
+        CK(cudaMalloc(&G.hostio, bytes));
+        G.hostio_bytes = bytes;
     }
-    if (g.hostio_i_bytes < ibytes) {
-        cudaFree(g.hostio_i);
-        g.hostio_i = nullptr; g.hostio_i_bytes = 0;
-        CK(cudaMalloc(&g.hostio_i, ibytes));
-        g.hostio_i_bytes = ibytes;
+    if (G.hostio_i_bytes < ibytes) {
+        cudaFree(G.hostio_i);
+        G.hostio_i = nullptr; G.hostio_i_bytes = 0;
+        CK(cudaMalloc(&G.hostio_i, ibytes));
+        G.hostio_i_bytes = ibytes;
     }
     return 0;
 }
@@ -543,13 +591,19 @@ const char *matinv_last_error(void) { return g_err; }
 
 void matinv_shutdown(void) {
     std::lock_guard<std::mutex> lk(g.mu);
-    if (!g.probed || g.ndev == 0 || g.device < 0) return;
+    if (!g.probed || g.ndev == 0) return;
     int cur = 0;
     cudaGetDevice(&cur);
-    if (cur != g.device) cudaSetDevice(g.device);
-    release_locked();
-    if (cur != g.device) cudaSetDevice(cur);
-    g.device = -1;
+    const int keep = g.cur;
+    for (int d = 0; d < g.ndev && d < MAX_DEVICES; d++) {
+        if (!g.dc[d].used) continue;
+        cudaSetDevice(d);
+        g.cur = d;
+        release_locked();
+        g.dc[d].used = false;
+    }
+    g.cur = keep;
+    cudaSetDevice(cur);
 }
 
 int matinv_invert_f32_dev(const float *A_dev, int n, float *X_dev, int *piv_dev, void *stream, int flags) {
@@ -572,25 +626,25 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
     const size_t bytes = (size_t)n * n * sizeof(float);
     rc = ensure_hostio(bytes, (size_t)n * sizeof(int));
     if (rc) return rc;
-    cudaStream_t st = g.stream;
-    CK(cudaMemcpyAsync(g.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(g.ev[0], st));
+    cudaStream_t st = G.stream;
+    CK(cudaMemcpyAsync(G.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(G.ev[0], st));
     if (flags & MATINV_FLAG_TF32X3) {
         // gated tensor-core path: A stays in hostio while X is written to a second buffer, then one D2H copy
-        if (g.hostx_bytes < bytes) {
-            cudaFree(g.hostx);
-            g.hostx = nullptr; g.hostx_bytes = 0;
-            CK(cudaMalloc(&g.hostx, bytes));
-            g.hostx_bytes = bytes;
+        if (G.hostx_bytes < bytes) {
+            cudaFree(G.hostx);
+            G.hostx = nullptr; G.hostx_bytes = 0;
+            CK(cudaMalloc(&G.hostx, bytes));
+            G.hostx_bytes = bytes;
         }
-        rc = invert_dev_locked(g.hostio, n, g.hostx, piv_host ? g.hostio_i : nullptr, st, flags);
+        rc = invert_dev_locked(G.hostio, n, G.hostx, piv_host ? G.hostio_i : nullptr, st, flags);
         if (rc < 0) return rc;
-        CK(cudaEventRecord(g.ev[1], st));
-        if (rc == MATINV_OK) CK(cudaMemcpyAsync(X_host, g.hostx, bytes, cudaMemcpyDeviceToHost, st));
-        if (piv_host) CK(cudaMemcpyAsync(piv_host, g.hostio_i, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(G.ev[1], st));
+        if (rc == MATINV_OK) CK(cudaMemcpyAsync(X_host, G.hostx, bytes, cudaMemcpyDeviceToHost, st));
+        if (piv_host) CK(cudaMemcpyAsync(piv_host, G.hostio_i, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+        CK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]));
         g_t_compute = ms * 1e-3;
         g_t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (flags & MATINV_FLAG_VERBOSE) {
@@ -600,33 +654,46 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
         }
         return rc;
     }
-    rc = factor_locked(g.hostio, n, st, flags);
+    rc = factor_locked(G.hostio, n, st, flags);
     if (rc) return rc;
     // extraction (deferred column permutation + isfinite scan) in row chunks, each chunk's D2H copy overlapped with the
     // extraction of the next one on a second stream -- replaces getInvertedMatrix + enqueueReadBuffer (LIB:369-381)
     rc = ensure_copy_stream();
     if (rc) return rc;
     {
-        Workspace &w = g.ws;
+        Workspace &w = G.ws;
         const int chunk = (n >= 4096) ? ((n + 15) / 16) : n;
         int ce = 0;
         for (int row0 = 0; row0 < n; row0 += chunk, ce ^= 1) {
             const int nrows = (n - row0 < chunk) ? n - row0 : chunk;
-            launch_extract_rows(w.W, w.npad, n, w.colsrc, g.hostio, w.info, !(flags & MATINV_FLAG_NOCHECK), row0, nrows, st);
+            launch_extract_rows(w.W, w.npad, n, w.colsrc, G.hostio, w.info, !(flags & MATINV_FLAG_NOCHECK), row0, nrows, st);
             COUNT_LAUNCH(1);
-            CK(cudaEventRecord(g.ev_chunk[ce], st));
-            CK(cudaStreamWaitEvent(g.copy_stream, g.ev_chunk[ce], 0));
-            CK(cudaMemcpyAsync(X_host + (size_t)row0 * n, g.hostio + (size_t)row0 * n, (size_t)nrows * n * sizeof(float),
-                               cudaMemcpyDeviceToHost, g.copy_stream));
+            cudaError_t e = cudaEventRecord(G.ev_chunk[ce], st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(G.copy_stream, G.ev_chunk[ce], 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(X_host + (size_t)row0 * n, G.hostio + (size_t)row0 * n, (size_t)nrows * n * sizeof(float),
+                                    cudaMemcpyDeviceToHost, G.copy_stream);
+            if (e != cudaSuccess) {
+                cudaStreamSynchronize(G.copy_stream);   // earlier chunks may still be in flight towards X_host
+                return fail(MATINV_E_CUDA, "chunked read-back -> %s", cudaGetErrorString(e));
+            }
         }
-        CK(cudaEventRecord(g.ev[1], st));
-        if (piv_host) CK(cudaMemcpyAsync(piv_host, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        {
+            cudaError_t e = cudaEventRecord(G.ev[1], st);
+            if (e == cudaSuccess && piv_host) e = cudaMemcpyAsync(piv_host, w.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) {
+                cudaStreamSynchronize(G.copy_stream);
+                return fail(MATINV_E_CUDA, "read-back -> %s", cudaGetErrorString(e));
+            }
+        }
     }
     rc = status_locked(st);
+    // the chunk copies write the caller's buffer: they must have drained on EVERY exit path (the caller may free it)
+    const cudaError_t ce = cudaStreamSynchronize(G.copy_stream);
     if (rc < 0) return rc;
-    CK(cudaStreamSynchronize(g.copy_stream));
+    if (ce != cudaSuccess) return fail(MATINV_E_CUDA, "cudaStreamSynchronize(copy stream) -> %s", cudaGetErrorString(ce));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+    CK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]));
     g_t_compute = ms * 1e-3;
     g_t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (flags & MATINV_FLAG_VERBOSE) {  // the reference's two stdout lines (LIB:385-386)
@@ -663,19 +730,23 @@ int matinv_invert_batched_f32(const float *A_host, int n, long long batch, float
     const size_t bytes = (size_t)batch * n * n * sizeof(float);
     rc = ensure_hostio(bytes, (size_t)batch * sizeof(int));
     if (rc) return rc;
-    cudaStream_t st = g.stream;
-    CK(cudaMemcpyAsync(g.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
-    CK(launch_batched(g.hostio, n, batch, g.hostio, g.hostio_i, st));
+    cudaStream_t st = G.stream;
+    CK(cudaMemcpyAsync(G.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
+    CK(launch_batched(G.hostio, n, batch, G.hostio, G.hostio_i, st));
     COUNT_LAUNCH(1);
-    CK(cudaMemcpyAsync(X_host, g.hostio, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(X_host, G.hostio, bytes, cudaMemcpyDeviceToHost, st));
+    std::vector<int> tmp;
     int *info = info_host;
-    int *tmp = nullptr;
-    if (!info) { tmp = (int *)malloc((size_t)batch * sizeof(int)); info = tmp; }
-    CK(cudaMemcpyAsync(info, g.hostio_i, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (!info) {
+        try { tmp.resize((size_t)batch); } catch (...) { cudaStreamSynchronize(st); return fail(MATINV_E_INVALID, "out of host memory"); }
+        info = tmp.data();
+    }
+    cudaError_t e = cudaMemcpyAsync(info, G.hostio_i, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st);
+    const cudaError_t es = cudaStreamSynchronize(st);   // X_host is being written: drain before any return
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) return fail(MATINV_E_CUDA, "batched read-back -> %s", cudaGetErrorString(e));
     int any = 0;
     for (long long b = 0; b < batch; b++) any |= (info[b] != 0);
-    free(tmp);
     return any ? MATINV_SINGULAR : MATINV_OK;
 }
 
@@ -711,8 +782,8 @@ int matinv_residual_f32_dev(const float *A_dev, const float *X_dev, int n, doubl
 }
 
 static int invert_f64_locked(const double *A_dev, int n, double *X_dev, int *piv_dev, cudaStream_t st, int flags) {
-    CK(f64_workspace_ensure(g.wsd, n, false));
-    F64Workspace &w = g.wsd;
+    CK(f64_workspace_ensure(G.wsd, n, false));
+    F64Workspace &w = G.wsd;
     const int nopiv = (flags & MATINV_FLAG_NOPIVOT) ? 1 : 0, check = !(flags & MATINV_FLAG_NOCHECK);
     if (flags & MATINV_FLAG_UNBLOCKED) {
         COUNT_LAUNCH(f64_invert_async(w, A_dev, n, X_dev, nopiv, check, st, g_prof.on ? prof_event : nullptr));
@@ -751,19 +822,19 @@ int matinv_invert_f64(const double *A_host, int n, double *X_host, int *piv_host
     const auto t0 = std::chrono::steady_clock::now();
     int rc = ensure_stream();
     if (rc) return rc;
-    CK(f64_workspace_ensure(g.wsd, n, true));
-    cudaStream_t st = g.stream;
+    CK(f64_workspace_ensure(G.wsd, n, true));
+    cudaStream_t st = G.stream;
     const size_t bytes = (size_t)n * n * sizeof(double);
-    CK(cudaMemcpyAsync(g.wsd.io, A_host, bytes, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(g.ev[0], st));
-    rc = invert_f64_locked(g.wsd.io, n, g.wsd.io, nullptr, st, flags);   // extraction reads W, so io may be overwritten
+    CK(cudaMemcpyAsync(G.wsd.io, A_host, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(G.ev[0], st));
+    rc = invert_f64_locked(G.wsd.io, n, G.wsd.io, nullptr, st, flags);   // extraction reads W, so io may be overwritten
     if (rc < 0) return rc;
-    CK(cudaEventRecord(g.ev[1], st));
-    CK(cudaMemcpyAsync(X_host, g.wsd.io, bytes, cudaMemcpyDeviceToHost, st));
-    if (piv_host) CK(cudaMemcpyAsync(piv_host, g.wsd.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(G.ev[1], st));
+    CK(cudaMemcpyAsync(X_host, G.wsd.io, bytes, cudaMemcpyDeviceToHost, st));
+    if (piv_host) CK(cudaMemcpyAsync(piv_host, G.wsd.piv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+    CK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]));
     g_t_compute = ms * 1e-3;
     g_t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (flags & MATINV_FLAG_VERBOSE) {
@@ -794,9 +865,9 @@ int matinv_host_defect_f64(const double *A_host, const double *B_host, int n, do
     double *dA = nullptr, *dB = nullptr;
     CK(cudaMalloc(&dA, bytes));
     if (cudaMalloc(&dB, bytes) != cudaSuccess) { cudaFree(dA); return fail(MATINV_E_CUDA, "cudaMalloc failed"); }
-    cudaError_t e = cudaMemcpyAsync(dA, A_host, bytes, cudaMemcpyHostToDevice, g.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dB, B_host, bytes, cudaMemcpyHostToDevice, g.stream);
-    if (e == cudaSuccess) e = run_residual_f64(dA, dB, n, out_host, g.stream);
+    cudaError_t e = cudaMemcpyAsync(dA, A_host, bytes, cudaMemcpyHostToDevice, G.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dB, B_host, bytes, cudaMemcpyHostToDevice, G.stream);
+    if (e == cudaSuccess) e = run_residual_f64(dA, dB, n, out_host, G.stream);
     cudaFree(dA);
     cudaFree(dB);
     if (e != cudaSuccess) return fail(MATINV_E_CUDA, "%s", cudaGetErrorString(e));
@@ -854,6 +925,23 @@ int matinv_probe_residual_f32_dev(const float *A_dev, const float *X_dev, int n,
     cudaFree(scratch);
     if (e != cudaSuccess) return fail(MATINV_E_CUDA, "probe residual: %s", cudaGetErrorString(e));
     return MATINV_OK;
+}
+
+int matinv_tf32x3_gate_dev(const float *A_dev, const float *X_dev, int n, double *est_out, void *stream) {
+    g_err[0] = 0;
+    if (n <= 0 || !A_dev || !X_dev) return fail(MATINV_E_INVALID, "invalid argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    double *scratch = nullptr;
+    CK(cudaMalloc(&scratch, probe_scratch_bytes(n)));
+    double r[3] = {0, 0, 0};
+    const cudaError_t e = run_probe_residual(A_dev, X_dev, n, scratch, r, (cudaStream_t)stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail(MATINV_E_CUDA, "probe residual: %s", cudaGetErrorString(e));
+    double est = 0.0, est_scaled = 0.0;
+    const bool ok = tf32x3_gate_accepts(r, n, &est, &est_scaled);
+    if (est_out) { est_out[0] = est; est_out[1] = est_scaled; }
+    return ok ? 1 : 0;
 }
 
 int matinv_tf32x3_status(double *last_estimate, int *last_fallback, long long *inversions, long long *fallbacks) {

@@ -40,6 +40,9 @@ extern "C" {
 
 /* Gate of MATINV_FLAG_TF32X3: estimate of ||A X - I||_F / (n ||A||_F ||X||_F) must not exceed this (north_star bound). */
 #define MATINV_TF32X3_GATE 1e-5
+/* ... and the same estimate times sqrt(n), which does not shrink with the order (the FP32 SIMT path measures ~3e-9), must
+ * not exceed this: without it the 1e-5 bound only rejects NaN and total garbage at large n (an unrelated X scores ~n^-1.5). */
+#define MATINV_TF32X3_GATE_SCALED 1e-7
 
 /* Replaces cl::Platform::get / getDevices (LIB:239-244).  Number of usable CUDA devices, 0 if none. */
 int matinv_device_count(void);
@@ -138,6 +141,11 @@ int matinv_profile_read(double *gemm_ms, long long *gemm_launches, double *gemm_
 /* O(n^2) randomised estimate of the same three numbers (4 Rademacher probe vectors: E ||(A X - I) v||^2 = ||A X - I||_F^2);
  * out_host[0] is an estimate, out_host[1..2] are exact.  This is what gates MATINV_FLAG_TF32X3. */
 int matinv_probe_residual_f32_dev(const float *A_dev, const float *X_dev, int n, double *out_host, void *stream);
+
+/* The gate of MATINV_FLAG_TF32X3 applied to a caller-provided pair (test hook / diagnostics): runs the O(n^2) probe and the
+ * acceptance rule the gated inversion uses.  est_out[2] (may be NULL) = {estimate, estimate * sqrt(n)}.  Returns 1 =
+ * accepted, 0 = rejected (NaN included), < 0 = error. */
+int matinv_tf32x3_gate_dev(const float *A_dev, const float *X_dev, int n, double *est_out, void *stream);
 
 /* MATINV_FLAG_TF32X3 bookkeeping: residual estimate of the last gated inversion (-1 if none), whether it fell back to
  * the FP32 SIMT schedule, and the totals since the library was loaded.  Any pointer may be NULL. */

@@ -314,12 +314,18 @@ void gj_generate_hollow_f32(float *A, int n, uint32_t *state) {
                             X[(size_t)r2 * ld + j] = elim_##SUF(X[(size_t)r2 * ld + j], C[(size_t)t * n + r2], u, nofma); \
                         }                                                                         \
                     }                                                                             \
-                    for (int i = 0; i < n; i++) { /* rank-sw trailing update inside the panel */ \
-                        if (i >= k0 + s0 && i < k0 + s0 + sw) continue;                           \
-                        T acc = X[(size_t)i * ld + j];                                            \
+                }                                                                                 \
+                /* rank-sw trailing update inside the panel, row by row (same per-element chain) */ \
+                _Pragma("omp parallel for schedule(static)")                                      \
+                for (int i = 0; i < n; i++) {                                                     \
+                    if (i >= k0 + s0 && i < k0 + s0 + sw) continue;                               \
+                    T *Xi = X + (size_t)i * ld;                                                   \
+                    for (int j = k0; j < k0 + kb; j++) {                                          \
+                        if (j >= k0 + s0 && j < k0 + s0 + sw) continue;                           \
+                        T acc = Xi[j];                                                            \
                         for (int t = s0; t < s0 + sw; t++)                                        \
                             acc = elim_##SUF(acc, C[(size_t)t * n + i], U[(size_t)t * n + j], nofma); \
-                        X[(size_t)i * ld + j] = acc;                                              \
+                        Xi[j] = acc;                                                              \
                     }                                                                             \
                 }                                                                                 \
             }                                                                                     \
@@ -333,40 +339,66 @@ void gj_generate_hollow_f32(float *A, int n, uint32_t *state) {
                     T x = X[r * ld + j]; X[r * ld + j] = X[p * ld + j]; X[p * ld + j] = x;        \
                 }                                                                                 \
             }                                                                                     \
-            _Pragma("omp parallel for schedule(static)")                                          \
-            for (int j = 0; j < n; j++) {                                                         \
-                if (j >= k0 && j < k0 + kb) continue;                                             \
+            /* row-block recurrence: per column j the steps t run in order (snapshot, then the other pivot rows);   \
+             * columns are independent, so they are processed in chunks with the row accesses contiguous */         \
+            _Pragma("omp parallel for schedule(dynamic, 1)")                                      \
+            for (int jc = 0; jc < n; jc += 256) {                                                 \
+                const int je = (jc + 256 < n) ? jc + 256 : n;                                     \
                 for (int t = 0; t < kb; t++) {                                                    \
-                    const int r = k0 + t;                                                         \
-                    const T u = X[(size_t)r * ld + j] / pv[t];                                    \
-                    U[(size_t)t * n + j] = u;                                                     \
-                    X[(size_t)r * ld + j] = u;                                                    \
+                    T *Xr = X + (size_t)(k0 + t) * ld;                                            \
+                    T *Ut = U + (size_t)t * n;                                                    \
+                    const T pvt = pv[t];                                                          \
+                    for (int j = jc; j < je; j++) {                                               \
+                        if (j >= k0 && j < k0 + kb) continue;                                     \
+                        const T u = Xr[j] / pvt;                                                  \
+                        Ut[j] = u;                                                                \
+                        Xr[j] = u;                                                                \
+                    }                                                                             \
                     for (int t2 = 0; t2 < kb; t2++) {                                             \
                         if (t2 == t) continue;                                                    \
-                        const int r2 = k0 + t2;                                                   \
-                        X[(size_t)r2 * ld + j] = elim_##SUF(X[(size_t)r2 * ld + j], C[(size_t)t * n + r2], u, nofma); \
+                        T *X2 = X + (size_t)(k0 + t2) * ld;                                       \
+                        const T c = C[(size_t)t * n + k0 + t2];                                   \
+                        for (int j = jc; j < je; j++) {                                           \
+                            if (j >= k0 && j < k0 + kb) continue;                                 \
+                            X2[j] = elim_##SUF(X2[j], c, Ut[j], nofma);                           \
+                        }                                                                         \
                     }                                                                             \
                 }                                                                                 \
             }                                                                                     \
-            _Pragma("omp parallel for schedule(static)")                                          \
+            /* per element: acc = X[i][j]; for t: acc = elim(acc, C[t][i], U[t][j]) -- the chain of A.3.  Loop order  \
+             * (row, column chunk, step, column) keeps the chunk in L1 and lets the compiler vectorise over j; the    \
+             * order of the operations on any ONE element is unchanged, so the result is bit-identical. */            \
+            _Pragma("omp parallel for schedule(dynamic, 16)")                                     \
             for (int i = 0; i < n; i++) {                                                         \
                 if (i >= k0 && i < k0 + kb) continue;                                             \
                 T *Xi = X + (size_t)i * ld;                                                       \
-                for (int j = 0; j < n; j++) {                                                     \
-                    if (j >= k0 && j < k0 + kb) continue;                                         \
-                    T acc = Xi[j];                                                                \
-                    for (int t = 0; t < kb; t++)                                                  \
-                        acc = elim_##SUF(acc, C[(size_t)t * n + i], U[(size_t)t * n + j], nofma); \
-                    Xi[j] = acc;                                                                  \
+                T ci[256];                                                                        \
+                for (int t = 0; t < kb; t++) ci[t] = C[(size_t)t * n + i];                        \
+                for (int seg = 0; seg < 2; seg++) {                                               \
+                    const int ja = seg ? k0 + kb : 0, jb = seg ? n : k0;                          \
+                    for (int jc = ja; jc < jb; jc += 1024) {                                      \
+                        const int je = (jc + 1024 < jb) ? jc + 1024 : jb;                         \
+                        for (int t = 0; t < kb; t++) {                                            \
+                            const T c = ci[t];                                                    \
+                            const T *Ut = U + (size_t)t * n;                                      \
+                            if (nofma) { for (int j = jc; j < je; j++) Xi[j] = elim_##SUF(Xi[j], c, Ut[j], 1); } \
+                            else {                                                                \
+                                _Pragma("omp simd")                                               \
+                                for (int j = jc; j < je; j++) Xi[j] = FMA(-c, Ut[j], Xi[j]);      \
+                            }                                                                     \
+                        }                                                                         \
+                    }                                                                             \
                 }                                                                                 \
             }                                                                                     \
         }                                                                                         \
         if (!info) {                                                                              \
-            for (int r = n - 1; r >= 0; r--) {                                                    \
-                int p = piv[r];                                                                   \
-                if (p == r) continue;                                                             \
-                for (int i = 0; i < n; i++) {                                                     \
-                    T t = X[i * ld + r]; X[i * ld + r] = X[i * ld + p]; X[i * ld + p] = t;        \
+            _Pragma("omp parallel for schedule(static)")                                          \
+            for (int i = 0; i < n; i++) {   /* the same transpositions, in the same order, one row at a time */ \
+                T *Xi = X + (size_t)i * ld;                                                       \
+                for (int r = n - 1; r >= 0; r--) {                                                \
+                    const int p = piv[r];                                                         \
+                    if (p == r) continue;                                                         \
+                    T t = Xi[r]; Xi[r] = Xi[p]; Xi[p] = t;                                        \
                 }                                                                                 \
             }                                                                                     \
             info = scan_finite_##SUF(X, ld * n);                                                  \

@@ -310,7 +310,9 @@ def test_tuning_switches_bit_identical(m):
     settings = [{}, {"MATINV_LOOKAHEAD": "0"}, {"MATINV_LOOKAHEAD": "1"}, {"MATINV_PANEL": "0"},
                 {"MATINV_UPDATE_ROWS": "256", "MATINV_ROWBLOCK_CW": "128", "MATINV_K1_THREADS": "256"},
                 {"MATINV_UPDATE_ROWS": "64", "MATINV_ROWBLOCK_CW": "32", "MATINV_K1_THREADS": "512", "MATINV_GEMM": "0"},
-                {"MATINV_BATCHED": "1", "MATINV_GEMM": "3"}, {"MATINV_BATCHED": "0", "MATINV_UPDATE_ROWS": "128"}]
+                {"MATINV_BATCHED": "1", "MATINV_GEMM": "3"}, {"MATINV_BATCHED": "0", "MATINV_UPDATE_ROWS": "128"},
+                {"MATINV_BATCHED": "3"}, {"MATINV_BATCHED": "4"}, {"MATINV_BATCHED": "4", "MATINV_BLK_CPS": "3"},
+                {"MATINV_SUBPANEL_SHAPE": "16x4x512"}, {"MATINV_SUBPANEL_SHAPE": "8x8x512"}]
     seen = []
     for extra in settings:
         env = {k: v for k, v in os.environ.items() if not k.startswith("MATINV_")}
@@ -329,3 +331,107 @@ def test_tuning_switches_bit_identical(m):
     Xo, po, io = o.invert_inplace(o.generate(1500, o.SEED_UNIFORM + 1500, "uniform"))
     assert io == 0
     assert hashlib.sha256(Xo.tobytes() + np.asarray(po, dtype=np.int32).tobytes()).hexdigest() == ref[0]
+
+
+_SHAPE_PROBE = r"""
+import sys
+import numpy as np, torch
+import gpu_matrix_inversion_b200 as m
+from oracle import gj_oracle as o
+for n in (int(a) for a in sys.argv[1:]):
+    A = o.uniform(n)
+    X, piv = m.invert(A, want_piv=True)
+    Xo, po, io = o.invert_inplace(A)
+    assert io == 0 and X is not None
+    assert np.array_equal(piv, po), ("pivots", n)
+    assert np.array_equal(X.view(np.uint32), Xo.view(np.uint32)), ("inverse", n)
+    S = A.copy(); S[:, 5] = 0.0
+    assert m.invert(S) is None and o.invert_inplace(S)[2] != 0
+print("SHAPE-OK")
+"""
+
+
+@pytest.mark.parametrize("shape", ["16x2x512", "16x4x256", "16x4x512", "8x8x512"])
+def test_subpanel_shapes_bit_identical(m, shape):
+    """The sub-panel kernel instantiations that only the large orders select -- <16,4,256> (N >= 15360), <16,4,512>
+    (16384 < N <= 32768) and <8,8,512> with 8-wide sub-panels (N > 32768, i.e. BASELINE config 5) -- forced through
+    MATINV_SUBPANEL_SHAPE at orders the oracle replays in seconds: pivot sequence and inverse bit for bit, ragged order
+    included (2100 is not a multiple of 128; 1100 goes through the schedule without look-ahead)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if not k.startswith("MATINV_")}
+    env["MATINV_SUBPANEL_SHAPE"] = shape
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    r = subprocess.run([sys.executable, "-c", _SHAPE_PROBE, "300", "1100", "2100"], env=env, cwd=root, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "SHAPE-OK" in r.stdout, r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n", [8320, 16384])
+def test_full_size_golden_hash(m, n):
+    """BASELINE config 3 at its full order: pivot sequence AND inverse of the N=16384 uniform workload (the matrix
+    bench.py inverts) bit for bit against the oracle, through a SHA-256 of piv || X that oracle/make_golden_large.py
+    computed with the blocked CPU replay and committed (tests/golden/large_sha256.json).  N=16384 runs the <16,4,256>
+    sub-panel shape and the 256-row in-panel update, N=8320 the shapes of the range below."""
+    import hashlib
+    import json
+    from pathlib import Path
+
+    import torch
+
+    gold = json.loads((Path(__file__).parent / "golden" / "large_sha256.json").read_text())
+    if str(n) not in gold:
+        pytest.skip(f"no golden hash for N={n} (run oracle/make_golden_large.py {n})")
+    g = gold[str(n)]
+    A = m.generate_dev(n, g["seed"], "uniform")
+    piv = torch.empty(n, dtype=torch.int32, device="cuda")
+    rc, X = m.invert_dev(A, piv=piv)
+    assert rc == m.OK, m.last_error()
+    ph = piv.cpu().numpy()
+    assert [int(p) for p in ph[:8]] == g["piv_head"]
+    h = hashlib.sha256(ph.tobytes() + X.cpu().numpy().tobytes()).hexdigest()
+    assert h == g["sha256_piv_X"]
+    res, _ = m.residual_dev(A, X)
+    assert res <= 1e-5
+
+
+_BIG_PROBE = r"""
+import hashlib, sys
+import torch
+import gpu_matrix_inversion_b200 as m
+from oracle.gj_oracle import SEED_UNIFORM
+n = int(sys.argv[1])
+A = m.generate_dev(n, SEED_UNIFORM + n, "uniform")
+piv = torch.empty(n, dtype=torch.int32, device="cuda")
+rc, X = m.invert_dev(A, piv=piv)
+assert rc == 0, m.last_error()
+est = m.probe_residual_dev(A, X)
+print("BIG", hashlib.sha256(piv.cpu().numpy().tobytes() + X.cpu().numpy().tobytes()).hexdigest(), est)
+"""
+
+
+def test_large_order_shapes_property(m):
+    """N=32896 (> 32768: the 8-wide <8,8,512> sub-panel kernel, 64-bit indexing past 2^31 bytes, a ragged last block):
+    the default cluster panel path and the per-column panel path (MATINV_PANEL=0, gj_panel.cu -- independent kernels, the
+    same arithmetic) must agree on SHA-256(piv || X), and the O(N^2) probe estimate of ||AX - I||_F / (N ||A||_F ||X||_F)
+    must pass north_star's 1e-5 bound.  The oracle cannot replay this order in test time; bit-exactness against it is
+    pinned for the same kernel instantiation at small orders by test_subpanel_shapes_bit_identical."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    for extra in ({}, {"MATINV_PANEL": "0"}):
+        env = {k: v for k, v in os.environ.items() if not k.startswith("MATINV_")}
+        env.update(extra)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        r = subprocess.run([sys.executable, "-c", _BIG_PROBE, "32896"], env=env, cwd=root, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, (extra, r.stderr[-3000:])
+        line = [l for l in r.stdout.splitlines() if l.startswith("BIG")][-1].split()
+        out.append((line[1], float(line[2])))
+    assert out[0][0] == out[1][0], out
+    assert out[0][1] <= 1e-5 and out[1][1] <= 1e-5, out

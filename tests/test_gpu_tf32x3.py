@@ -177,3 +177,29 @@ def test_full_size_properties_n8192(m, torch):
     rc, A2 = m.invert_dev(X, flags=m.FLAG_TF32X3)
     assert rc == m.OK
     assert float((A2 - A).norm() / A.norm()) < 1e-3
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_gate_rejects_plausible_but_wrong_inverses(m, torch, n):
+    """The acceptance rule must constrain the result at the orders where the tensor-core path matters.  north_star's
+    ||AX-I||_F / (n ||A||_F ||X||_F) <= 1e-5 alone does not (an X unrelated to inv(A) scores ~n^-1.5), so the gate also
+    bounds the estimate times sqrt(n) (MATINV_TF32X3_GATE_SCALED): the inverse of a DIFFERENT random matrix, a true inverse
+    with 1 % relative noise and one with 0.1 % noise are rejected (such noise scores eps / n on the scaled estimate), the FP32 SIMT inverse and the tensor-core inverse of the
+    same matrix are accepted."""
+    A = m.generate_dev(n, o.SEED_UNIFORM + n, "uniform")
+    rc, X = m.invert_dev(A)
+    assert rc == m.OK
+    ok, est, est_s = m.tf32x3_gate_dev(A, X)
+    assert ok and est <= m.TF32X3_GATE and est_s <= m.TF32X3_GATE_SCALED, (est, est_s)
+    rc, Xt = m.invert_dev(A, torch.empty_like(A), flags=m.FLAG_TF32X3)
+    assert rc == m.OK and not m.tf32x3_status()["fell_back"]
+    assert m.tf32x3_gate_dev(A, Xt)[0]
+    B = m.generate_dev(n, o.SEED_UNIFORM + n + 12345, "uniform")
+    rc, Xb = m.invert_dev(B)
+    ok, est, est_s = m.tf32x3_gate_dev(A, Xb)                 # inverse of another matrix: passes 1e-5, fails the scaled bound
+    assert not ok and est_s > m.TF32X3_GATE_SCALED, (est, est_s)
+    g = torch.Generator(device="cuda").manual_seed(n)
+    for rel in (1e-2, 1e-3):
+        noise = 1.0 + rel * torch.randn(X.shape, device="cuda", generator=g)
+        ok, est, est_s = m.tf32x3_gate_dev(A, X * noise)
+        assert not ok, (rel, est, est_s)
