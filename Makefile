@@ -20,7 +20,7 @@ $(CSRC)/matrix_inversion.o: $(CSRC)/matrix_inversion.cpp include/matrix_inversio
 	g++ -O2 -std=c++17 -fPIC -c $< -o $@
 
 $(OUT): $(OBJ)
-	$(NVCC) -shared -o $@ $(OBJ) -gencode arch=compute_100a,code=sm_100a -lcudart
+	$(NVCC) -shared -o $@ $(OBJ) -gencode arch=compute_100a,code=sm_100a -lcudart -ldl
 
 oracle:
 	gcc -O3 -mfma -mavx2 -ffp-contract=off -fopenmp -fPIC -shared -o oracle/libgj_oracle.so oracle/gj_oracle.c -lm

@@ -21,7 +21,8 @@ import numpy as np
 
 __all__ = ["lib", "matrix_inv_32", "invert", "invert_dev", "invert_batched", "invert_batched_dev", "device_count",
            "last_error", "last_timing", "MatinvError", "OK", "SINGULAR", "FLAG_UNBLOCKED", "FLAG_VERBOSE",
-           "FLAG_NOCHECK", "FLAG_TF32X3", "TF32X3_GATE", "tf32x3_status", "debug_trailing_update", "probe_residual_dev", "tf32x3_gate_dev", "TF32X3_GATE_SCALED", "EXPORTS"]
+           "FLAG_NOCHECK", "FLAG_TF32X3", "TF32X3_GATE", "tf32x3_status", "debug_trailing_update", "probe_residual_dev", "tf32x3_gate_dev", "TF32X3_GATE_SCALED", "invert_sharded", "sharded_synthetic",
+           "invert_batched_ngpu", "EXPORTS"]
 
 OK, SINGULAR = 0, 1
 E_INVALID, E_NODEVICE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
@@ -40,7 +41,8 @@ EXPORTS = [
     "matinv_shard_apply", "matinv_shard_apply_ex", "matinv_shard_status", "matinv_generate_f32_dev", "matinv_generate_batched_f32_dev",
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
     "matinv_profile_read", "matinv_debug_trace", "matinv_invert_f64", "matinv_invert_f64_dev", "matinv_residual_f64_dev",
-    "matinv_host_defect_f64", "matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev", "matinv_tf32x3_gate_dev",
+    "matinv_host_defect_f64", "matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev", "matinv_tf32x3_gate_dev", "matinv_invert_sharded_f32", "matinv_sharded_synthetic_f32",
+    "matinv_invert_batched_f32_ngpu", "matinv_nccl_version",
 ]
 
 
@@ -101,6 +103,12 @@ def _load() -> ctypes.CDLL:
     L.matinv_debug_trailing_update.argtypes = [fp, ll, i, i, fp, fp, i, i, dp, vp]
     L.matinv_probe_residual_f32_dev.argtypes = [fp, fp, i, dp, vp]
     L.matinv_tf32x3_gate_dev.argtypes = [fp, fp, i, dp, vp]
+    L.matinv_invert_sharded_f32.argtypes = [fp, i, fp, ip, i, i, i]
+    L.matinv_sharded_synthetic_f32.argtypes = [i, ull, i, i, ip, dp]
+    L.matinv_invert_batched_f32_ngpu.argtypes = [fp, i, ll, fp, ip, i, i]
+    L.matinv_nccl_version.argtypes = []
+    for name in ("matinv_invert_sharded_f32", "matinv_sharded_synthetic_f32", "matinv_invert_batched_f32_ngpu", "matinv_nccl_version"):
+        getattr(L, name).restype = i
     for name in ("matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev", "matinv_tf32x3_gate_dev"):
         getattr(L, name).restype = i
     for name in ("matinv_invert_f32", "matinv_invert_f32_dev", "matinv_invert_batched_f32",
@@ -264,6 +272,38 @@ def invert_batched(A: np.ndarray, flags: int = 0):
     X = np.empty_like(A)
     info = np.empty(b, dtype=np.int32)
     _check(lib.matinv_invert_batched_f32(A.ctypes.data, n, b, X.ctypes.data, info.ctypes.data, flags))
+    return X, info
+
+
+def invert_sharded(A: np.ndarray, ngpu: int = 0, flags: int = 0, want_piv: bool = False):
+    """One inversion column-sharded over `ngpu` GPUs of this process (matinv_invert_sharded_f32; ngpu = 0: MATINV_NGPU or
+    every visible device).  Same return convention as invert(): X or None when singular, bit-identical to invert()."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    n = A.shape[0]
+    assert A.shape == (n, n)
+    X = np.empty_like(A)
+    piv = np.empty(n, dtype=np.int32)
+    rc = _check(lib.matinv_invert_sharded_f32(A.ctypes.data, n, X.ctypes.data, piv.ctypes.data, ngpu, 0, flags))
+    Xr = X if rc == OK else None
+    return (Xr, piv) if want_piv else Xr
+
+
+def sharded_synthetic(n: int, seed: int, kind: str = "uniform", ngpu: int = 0):
+    """Column-sharded inversion of the synthetic workload generated on the devices: (rc, piv, compute_ms)."""
+    piv = np.empty(n, dtype=np.int32)
+    ms = ctypes.c_double(-1.0)
+    rc = _check(lib.matinv_sharded_synthetic_f32(n, seed, 1 if kind == "diagdom" else 0, ngpu, piv.ctypes.data, ctypes.byref(ms)))
+    return rc, piv, ms.value
+
+
+def invert_batched_ngpu(A: np.ndarray, ngpu: int = 0, flags: int = 0):
+    """Batched small-n inversion split by matrix index over `ngpu` GPUs (no communication): (X, info)."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    b, n, n2 = A.shape
+    assert n == n2
+    X = np.empty_like(A)
+    info = np.empty(b, dtype=np.int32)
+    _check(lib.matinv_invert_batched_f32_ngpu(A.ctypes.data, n, b, X.ctypes.data, info.ctypes.data, ngpu, flags))
     return X, info
 
 

@@ -1,0 +1,588 @@
+// Single-call multi-GPU entries of the C-ABI: one process, one host thread per GPU, NCCL for the exchange.
+//
+//   matinv_invert_sharded_f32       one large matrix, 1-D block-cyclic column sharding (north_star:
+//                                   "single large N uses 1-D block-cyclic column sharding ... broadcast over NVLink via NCCL")
+//   matinv_invert_batched_f32_ngpu  batched small-n inversions split by matrix index, no communication
+//
+// The reference is single-device by construction (/root/reference/Matlab/mat_inv_32/mat_inv_32/mat_inv_32.cpp:239-250:
+// platforms[0] / devices[0], one in-order queue); these entries are what `matrix_inv_32` reaches when MATINV_NGPU > 1, so a
+// C++ / Matlab caller gets more than one GPU behind the unchanged header.
+//
+// Sharded schedule = the per-rank primitives of gj_sharded.cu (matinv_shard_factor / _apply_ex: the same kernels and FMA
+// chains as the single-GPU path, hence a bit-identical result) driven exactly like the torchrun host loop of
+// gpu_matrix_inversion_b200/sharded.py:_factorize_lookahead, with ncclBroadcast on a high-priority side stream:
+//   per 128-column block J:  owner(J+1) updates block J+1 first, factors it on the side stream and starts its broadcast
+//                            while every rank (itself included) applies panel J to the remaining columns.
+// After the last block the deferred column permutation X[:, j] = M[:, colsrc[j]] moves columns between ranks: a gather
+// kernel packs, per destination rank, the columns it needs (row-major n x count), one grouped ncclSend / ncclRecv exchanges
+// them, a scatter kernel places them.
+//
+// NCCL is loaded with dlopen at first use (libnccl.so.2: the copy already in the process if torch is loaded, else the
+// system one), so libmatinv32.so keeps loading on machines without NCCL; there the multi-GPU entries return
+// MATINV_E_UNSUPPORTED for ngpu > 1.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/matinv_shim.h"
+#include "common.cuh"
+#include "kernels.h"
+
+int shim_fail(int code, const char *fmt, ...);
+int shim_device_count();
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- NCCL, loaded lazily
+struct Nccl {
+    void *h = nullptr;
+    bool tried = false;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclCommAbort) CommAbort = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+} g_nccl;
+
+bool nccl_load() {
+    if (g_nccl.tried) return g_nccl.h != nullptr;
+    g_nccl.tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return false;
+#define NCCL_SYM(field, name)                                   \
+    g_nccl.field = (decltype(g_nccl.field))dlsym(h, #name);     \
+    if (!g_nccl.field) { dlclose(h); return false; }
+    NCCL_SYM(CommInitAll, ncclCommInitAll)
+    NCCL_SYM(CommDestroy, ncclCommDestroy)
+    NCCL_SYM(CommAbort, ncclCommAbort)
+    NCCL_SYM(Broadcast, ncclBroadcast)
+    NCCL_SYM(Send, ncclSend)
+    NCCL_SYM(Recv, ncclRecv)
+    NCCL_SYM(GroupStart, ncclGroupStart)
+    NCCL_SYM(GroupEnd, ncclGroupEnd)
+    NCCL_SYM(GetErrorString, ncclGetErrorString)
+    NCCL_SYM(GetVersion, ncclGetVersion)
+#undef NCCL_SYM
+    g_nccl.h = h;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------- column exchange kernels
+// sendbuf[i * cnt + k] = Wl[i * ld + cols[k]]   (row-major n x cnt, one thread per element)
+__global__ void pack_columns_kernel(const float *__restrict__ Wl, long long ld, int n, const int *__restrict__ cols, int cnt,
+                                    float *__restrict__ out) {
+    const long long total = (long long)n * cnt;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / cnt;
+        const int k = (int)(e - i * cnt);
+        out[e] = Wl[i * ld + cols[k]];
+    }
+}
+// Out[i * ld + cols[k]] = recvbuf[i * cnt + k]
+__global__ void unpack_columns_kernel(float *__restrict__ Out, long long ld, int n, const int *__restrict__ cols, int cnt,
+                                      const float *__restrict__ in) {
+    const long long total = (long long)n * cnt;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / cnt;
+        const int k = (int)(e - i * cnt);
+        Out[i * ld + cols[k]] = in[e];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- helpers
+struct Barrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int count, waiting = 0, gen = 0;
+    explicit Barrier(int n) : count(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        const int my = gen;
+        if (++waiting == count) {
+            waiting = 0;
+            gen++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != my; });
+        }
+    }
+};
+
+// colsrc with X[:, j] = M[:, colsrc[j]]: net effect of `for r = n-1..0: swap columns r, piv[r]` (SURVEY.md Appendix A.3;
+// device twin csrc/gj_finish.cu:colperm_kernel, Python twin sharded.py:column_gather_list)
+void column_gather_list(const int *piv, int n, std::vector<int> &idx) {
+    idx.resize(n);
+    for (int j = 0; j < n; j++) idx[j] = j;
+    for (int r = n - 1; r >= 0; r--) {
+        const int p = piv[r];
+        if (p != r) std::swap(idx[r], idx[p]);
+    }
+}
+
+struct Comms {
+    std::mutex mu;
+    int ngpu = 0;
+    std::vector<ncclComm_t> comm;
+} g_comms;
+
+int ensure_comms(int ngpu) {
+    if (g_comms.ngpu == ngpu) return 0;
+    if (!nccl_load()) return shim_fail(MATINV_E_UNSUPPORTED, "NCCL (libnccl.so.2) is not available: multi-GPU entries need it");
+    if (g_comms.ngpu) {
+        for (ncclComm_t c : g_comms.comm) g_nccl.CommDestroy(c);
+        g_comms.comm.clear();
+        g_comms.ngpu = 0;
+    }
+    std::vector<int> devs(ngpu);
+    for (int d = 0; d < ngpu; d++) devs[d] = d;
+    g_comms.comm.resize(ngpu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    const ncclResult_t r = g_nccl.CommInitAll(g_comms.comm.data(), ngpu, devs.data());
+    cudaSetDevice(cur);
+    if (r != ncclSuccess) {
+        g_comms.comm.clear();
+        return shim_fail(MATINV_E_CUDA, "ncclCommInitAll(%d) -> %s", ngpu, g_nccl.GetErrorString(r));
+    }
+    g_comms.ngpu = ngpu;
+    return 0;
+}
+
+struct RankState {
+    matinv_shard_t *sh = nullptr;
+    void *msg[2] = {nullptr, nullptr};
+    cudaStream_t main = nullptr, side = nullptr;
+    cudaEvent_t ev_top = nullptr, ev_ready = nullptr, ev_done = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    float *sendbuf = nullptr, *recvbuf = nullptr, *Out = nullptr;
+    int *cols_dev = nullptr;
+    int rc = 0;
+    char err[256] = "";
+};
+
+#define RCK(call)                                                                                              \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess) {                                                                              \
+            snprintf(S.err, sizeof(S.err), "%s -> %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            S.rc = MATINV_E_CUDA;                                                                              \
+            return;                                                                                            \
+        }                                                                                                      \
+    } while (0)
+#define RNK(call)                                                                                              \
+    do {                                                                                                       \
+        ncclResult_t e__ = (call);                                                                             \
+        if (e__ != ncclSuccess) {                                                                              \
+            snprintf(S.err, sizeof(S.err), "%s -> %s (%s:%d)", #call, g_nccl.GetErrorString(e__), __FILE__, __LINE__); \
+            S.rc = MATINV_E_CUDA;                                                                              \
+            return;                                                                                            \
+        }                                                                                                      \
+    } while (0)
+#define RMK(call)                                                                                              \
+    do {                                                                                                       \
+        const int rc__ = (call);                                                                               \
+        if (rc__ < 0) {                                                                                        \
+            snprintf(S.err, sizeof(S.err), "%s -> %d: %s", #call, rc__, matinv_last_error());                  \
+            S.rc = rc__;                                                                                       \
+            return;                                                                                            \
+        }                                                                                                      \
+    } while (0)
+
+void rank_release(RankState &S) {
+    if (S.sh) matinv_shard_destroy(S.sh);
+    cudaFree(S.msg[0]); cudaFree(S.msg[1]); cudaFree(S.sendbuf); cudaFree(S.recvbuf); cudaFree(S.Out); cudaFree(S.cols_dev);
+    if (S.ev_top) cudaEventDestroy(S.ev_top);
+    if (S.ev_ready) cudaEventDestroy(S.ev_ready);
+    if (S.ev_done) cudaEventDestroy(S.ev_done);
+    if (S.ev_t0) cudaEventDestroy(S.ev_t0);
+    if (S.ev_t1) cudaEventDestroy(S.ev_t1);
+    if (S.main) cudaStreamDestroy(S.main);
+    if (S.side) cudaStreamDestroy(S.side);
+    S = RankState();
+}
+
+struct Shared {
+    int n, ngpu, nblk;
+    const float *A_host;
+    float *X_host;
+    int flags;
+    unsigned long long gen_seed;   // A_host == NULL: synthetic workload generated on the devices (timing runs)
+    int gen_kind;
+    Barrier bar;
+    std::vector<int> piv;          // rank 0's copy after the factorisation
+    std::vector<int> colsrc;
+    int info = 0;
+    bool exchange = true;          // apply the deferred column permutation across ranks (false: factorisation only)
+    double compute_ms = 0.0;
+    Shared(int g) : bar(g) {}
+};
+
+int owner_of(int J, int world) { return J % world; }
+// position of global column c inside its owner's local storage
+long long local_index(int c, int world) { return (long long)(c / MATINV_NB / world) * MATINV_NB + c % MATINV_NB; }
+
+// Phase 1 (per rank): allocate, upload, factorise.  Phase 2 after a barrier: column exchange + download.
+void rank_factor(int g, Shared &sh, RankState &S) {
+    const int n = sh.n, G = sh.ngpu, nblk = sh.nblk;
+    RCK(cudaSetDevice(g));
+    int lo = 0, hi = 0;
+    RCK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RCK(cudaStreamCreateWithFlags(&S.main, cudaStreamNonBlocking));
+    RCK(cudaStreamCreateWithPriority(&S.side, cudaStreamNonBlocking, hi));
+    RCK(cudaEventCreateWithFlags(&S.ev_top, cudaEventDisableTiming));
+    RCK(cudaEventCreateWithFlags(&S.ev_ready, cudaEventDisableTiming));
+    RCK(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+    RCK(cudaEventCreate(&S.ev_t0));
+    RCK(cudaEventCreate(&S.ev_t1));
+    RMK(matinv_shard_create(n, g, G, &S.sh));
+    const long long mbytes = matinv_shard_panel_bytes(n);
+    RCK(cudaMalloc(&S.msg[0], (size_t)mbytes));
+    RCK(cudaMalloc(&S.msg[1], (size_t)mbytes));
+    RCK(cudaMemset(S.msg[0], 0, (size_t)mbytes));
+    RCK(cudaMemset(S.msg[1], 0, (size_t)mbytes));
+    {   // exchange buffers (column permutation): at most every local column leaves and as many arrive
+        long long lcols = 0, lld = 0;
+        matinv_shard_local(S.sh, &lcols, &lld);
+        const size_t cnt = (size_t)std::max<long long>(lcols, 1);
+        RCK(cudaMalloc(&S.cols_dev, 2 * cnt * sizeof(int)));
+        if (sh.exchange) {
+            RCK(cudaMalloc(&S.sendbuf, cnt * n * sizeof(float)));
+            RCK(cudaMalloc(&S.recvbuf, cnt * n * sizeof(float)));
+            RCK(cudaMalloc(&S.Out, cnt * n * sizeof(float)));
+        }
+    }
+    if (sh.A_host) {
+        for (int J = g; J < nblk; J += G) RMK(matinv_shard_set_block(S.sh, J, sh.A_host + (size_t)J * MATINV_NB, n, S.main));
+    } else {
+        RMK(matinv_shard_generate(S.sh, sh.gen_seed, sh.gen_kind, S.main));
+    }
+    RCK(cudaStreamSynchronize(S.main));
+}
+
+void rank_schedule(int g, Shared &sh, RankState &S) {
+    const int G = sh.ngpu, nblk = sh.nblk;
+    ncclComm_t comm = (G > 1) ? g_comms.comm[g] : nullptr;
+    const size_t mbytes = (size_t)matinv_shard_panel_bytes(sh.n);
+    RCK(cudaSetDevice(g));
+    RCK(cudaEventRecord(S.ev_t0, S.main));
+    if (owner_of(0, G) == g) RMK(matinv_shard_factor(S.sh, 0, S.msg[0], S.main));
+    if (G > 1) RNK(g_nccl.Broadcast(S.msg[0], S.msg[0], mbytes, ncclChar, owner_of(0, G), comm, S.main));
+    for (int J = 0; J < nblk; J++) {
+        void *msg = S.msg[J & 1];
+        const int nxt = J + 1;
+        if (nxt >= nblk) {
+            RMK(matinv_shard_apply(S.sh, J, msg, S.main));
+            break;
+        }
+        void *nmsg = S.msg[nxt & 1];
+        const int own_n = owner_of(nxt, G);
+        RCK(cudaEventRecord(S.ev_top, S.main));     // everything that read nmsg (the apply of panel J-1) is before this point
+        if (own_n == g) {
+            RMK(matinv_shard_apply_ex(S.sh, J, msg, S.main, 1, nxt));
+            RCK(cudaEventRecord(S.ev_ready, S.main));
+            RCK(cudaStreamWaitEvent(S.side, S.ev_ready, 0));
+            RMK(matinv_shard_factor(S.sh, nxt, nmsg, S.side));
+            if (G > 1) RNK(g_nccl.Broadcast(nmsg, nmsg, mbytes, ncclChar, own_n, comm, S.side));
+            RMK(matinv_shard_apply_ex(S.sh, J, msg, S.main, 2, nxt));
+        } else {
+            RCK(cudaStreamWaitEvent(S.side, S.ev_top, 0));
+            RNK(g_nccl.Broadcast(nmsg, nmsg, mbytes, ncclChar, own_n, comm, S.side));
+            RMK(matinv_shard_apply(S.sh, J, msg, S.main));
+        }
+        RCK(cudaEventRecord(S.ev_done, S.side));
+        RCK(cudaStreamWaitEvent(S.main, S.ev_done, 0));
+    }
+    RCK(cudaEventRecord(S.ev_t1, S.main));
+}
+
+void rank_status(int g, Shared &sh, RankState &S, std::vector<int> &piv, int &info) {
+    RCK(cudaSetDevice(g));
+    piv.resize(sh.n);
+    const int rc = matinv_shard_status(S.sh, &info, piv.data(), S.main);
+    if (rc < 0) {
+        snprintf(S.err, sizeof(S.err), "matinv_shard_status -> %d: %s", rc, matinv_last_error());
+        S.rc = rc;
+    }
+}
+
+// Deferred column permutation across ranks + download of the local blocks of X (or, device-resident runs, nothing to
+// download).  colsrc is shared (computed once by rank 0 from the pivot sequence every rank holds identically).
+void rank_exchange(int g, Shared &sh, RankState &S) {
+    const int n = sh.n, G = sh.ngpu, nblk = sh.nblk;
+    ncclComm_t comm = (G > 1) ? g_comms.comm[g] : nullptr;
+    RCK(cudaSetDevice(g));
+    long long lcols = 0, lld = 0;
+    float *Wl = matinv_shard_local(S.sh, &lcols, &lld);
+    if (lcols == 0) return;
+    // per peer: the local source columns I send (increasing destination column order) and the local slots I receive into
+    std::vector<std::vector<int>> send_cols(G), recv_cols(G);
+    for (int j = 0; j < n; j++) {
+        const int src = sh.colsrc[j];
+        const int sr = owner_of(src / MATINV_NB, G), dr = owner_of(j / MATINV_NB, G);
+        if (sr == g) send_cols[dr].push_back((int)local_index(src, G));
+        if (dr == g) recv_cols[sr].push_back((int)local_index(j, G));
+    }
+    size_t tot_send = 0, tot_recv = 0;
+    std::vector<size_t> soff(G), roff(G);
+    std::vector<int> flat;
+    for (int p = 0; p < G; p++) { soff[p] = tot_send; tot_send += send_cols[p].size(); }
+    for (int p = 0; p < G; p++) { roff[p] = tot_recv; tot_recv += recv_cols[p].size(); }
+    for (int p = 0; p < G; p++) flat.insert(flat.end(), send_cols[p].begin(), send_cols[p].end());
+    for (int p = 0; p < G; p++) flat.insert(flat.end(), recv_cols[p].begin(), recv_cols[p].end());
+    RCK(cudaMemcpyAsync(S.cols_dev, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, S.main));
+    for (int p = 0; p < G; p++) {
+        const int cnt = (int)send_cols[p].size();
+        if (!cnt) continue;
+        const long long total = (long long)n * cnt;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        pack_columns_kernel<<<blocks, 256, 0, S.main>>>(Wl, lld, n, S.cols_dev + soff[p], cnt, S.sendbuf + soff[p] * n);
+    }
+    RCK(cudaGetLastError());
+    if (G > 1) {
+        RNK(g_nccl.GroupStart());
+        for (int p = 0; p < G; p++) {
+            if (p == g) continue;
+            if (!send_cols[p].empty()) RNK(g_nccl.Send(S.sendbuf + soff[p] * n, send_cols[p].size() * (size_t)n, ncclFloat, p, comm, S.main));
+            if (!recv_cols[p].empty()) RNK(g_nccl.Recv(S.recvbuf + roff[p] * n, recv_cols[p].size() * (size_t)n, ncclFloat, p, comm, S.main));
+        }
+        RNK(g_nccl.GroupEnd());
+    }
+    if (!send_cols[g].empty())
+        RCK(cudaMemcpyAsync(S.recvbuf + roff[g] * n, S.sendbuf + soff[g] * n, send_cols[g].size() * (size_t)n * sizeof(float),
+                            cudaMemcpyDeviceToDevice, S.main));
+    for (int p = 0; p < G; p++) {
+        const int cnt = (int)recv_cols[p].size();
+        if (!cnt) continue;
+        const long long total = (long long)n * cnt;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        unpack_columns_kernel<<<blocks, 256, 0, S.main>>>(S.Out, lcols, n, S.cols_dev + tot_send + roff[p], cnt, S.recvbuf + roff[p] * n);
+    }
+    RCK(cudaGetLastError());
+    RCK(cudaEventRecord(S.ev_t1, S.main));      // end of the device-resident window (factorisation + column exchange)
+    if (sh.X_host) {
+        for (int J = g; J < nblk; J += G) {
+            const int ncols = std::min(MATINV_NB, n - J * MATINV_NB);
+            RCK(cudaMemcpy2DAsync(sh.X_host + (size_t)J * MATINV_NB, (size_t)n * sizeof(float), S.Out + (size_t)(J / G) * MATINV_NB,
+                                  (size_t)lcols * sizeof(float), (size_t)ncols * sizeof(float), n, cudaMemcpyDeviceToHost, S.main));
+        }
+    }
+    RCK(cudaStreamSynchronize(S.main));
+}
+
+thread_local double g_last_sharded_ms = -1.0;
+
+int run_sharded(const float *A_host, int n, float *X_host, int *piv_host, int ngpu, int flags, unsigned long long gen_seed,
+                int gen_kind, bool exchange) {
+    const int ndev = shim_device_count();
+    if (ndev == 0) return shim_fail(MATINV_E_NODEVICE, "no CUDA device");
+    if (ngpu <= 0) {
+        const char *e = getenv("MATINV_NGPU");
+        ngpu = e ? atoi(e) : ndev;
+        if (ngpu <= 0) ngpu = ndev;
+    }
+    if (ngpu > ndev) return shim_fail(MATINV_E_INVALID, "ngpu = %d but only %d CUDA device(s) are visible", ngpu, ndev);
+    const int nblk = (n + MATINV_NB - 1) / MATINV_NB;
+    if (ngpu > nblk) ngpu = nblk;   // a rank without columns has nothing to do
+    std::lock_guard<std::mutex> lk(g_comms.mu);   // one multi-GPU call at a time (the communicators are shared)
+    if (ngpu > 1) {
+        const int rc = ensure_comms(ngpu);
+        if (rc) return rc;
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    Shared sh(ngpu);
+    sh.n = n; sh.ngpu = ngpu; sh.nblk = nblk; sh.A_host = A_host; sh.X_host = X_host; sh.flags = flags;
+    sh.gen_seed = gen_seed; sh.gen_kind = gen_kind; sh.exchange = exchange;
+    std::vector<RankState> st(ngpu);
+    std::vector<std::vector<int>> pivs(ngpu);
+    std::vector<int> infos(ngpu, 0);
+    auto any_failed = [&]() {
+        for (int g = 0; g < ngpu; g++) if (st[g].rc < 0) return true;
+        return false;
+    };
+    auto body = [&](int g) {
+        RankState &S = st[g];
+        rank_factor(g, sh, S);
+        sh.bar.wait();
+        const bool ok1 = !any_failed();          // every rank sees the same verdict: all ranks wrote rc before the barrier
+        if (ok1) rank_schedule(g, sh, S);
+        if (ok1 && S.rc == 0) rank_status(g, sh, S, pivs[g], infos[g]);
+        sh.bar.wait();
+        const bool ok2 = ok1 && !any_failed();
+        if (ok2 && g == 0) {
+            sh.info = infos[0];
+            for (int r = 1; r < ngpu; r++)
+                if (infos[r] != infos[0] || pivs[r] != pivs[0]) {
+                    snprintf(S.err, sizeof(S.err), "ranks disagree on the pivot sequence / status word");
+                    S.rc = MATINV_E_CUDA;
+                }
+            if (S.rc == 0 && sh.info == 0) column_gather_list(pivs[0].data(), n, sh.colsrc);
+        }
+        sh.bar.wait();
+        if (ok2 && !any_failed() && sh.info == 0 && sh.exchange) rank_exchange(g, sh, S);
+        if (S.rc == 0 && g == 0 && ok2) {
+            float ms = 0.f;
+            cudaSetDevice(0);
+            if (cudaEventSynchronize(S.ev_t1) == cudaSuccess && cudaEventElapsedTime(&ms, S.ev_t0, S.ev_t1) == cudaSuccess) sh.compute_ms = ms;
+        }
+        sh.bar.wait();
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < ngpu; g++) th.emplace_back(body, g);
+    body(0);
+    for (auto &t : th) t.join();
+    int rc = 0;
+    char msg[320] = "";
+    for (int g = 0; g < ngpu; g++)
+        if (st[g].rc < 0 && rc == 0) {
+            rc = st[g].rc;
+            snprintf(msg, sizeof(msg), "GPU %d: %s", g, st[g].err);
+        }
+    if (rc == 0 && piv_host) memcpy(piv_host, pivs[0].data(), (size_t)n * sizeof(int));
+    g_last_sharded_ms = (rc == 0) ? sh.compute_ms : -1.0;
+    for (int g = 0; g < ngpu; g++) {
+        cudaSetDevice(g);
+        rank_release(st[g]);
+    }
+    cudaSetDevice(cur);
+    if (rc < 0) {
+        if (ngpu > 1) {   // a failed rank may have left collectives half-issued: the communicators are not reusable
+            for (ncclComm_t c : g_comms.comm) g_nccl.CommAbort(c);
+            g_comms.comm.clear();
+            g_comms.ngpu = 0;
+        }
+        return shim_fail(rc, "%s", msg);
+    }
+    if (sh.info != 0) {
+        if (sh.info > 0) return shim_fail(MATINV_SINGULAR, "singular: zero or non-finite pivot at column %d", sh.info - 1);
+        return shim_fail(MATINV_SINGULAR, "singular: non-finite entry in the inverse");
+    }
+    return MATINV_OK;
+}
+
+}  // namespace
+
+void multi_shutdown() {
+    std::lock_guard<std::mutex> lk(g_comms.mu);
+    if (g_comms.ngpu && g_nccl.h) {
+        for (ncclComm_t c : g_comms.comm) g_nccl.CommDestroy(c);
+    }
+    g_comms.comm.clear();
+    g_comms.ngpu = 0;
+}
+
+extern "C" {
+
+int matinv_nccl_version(void) {
+    if (!nccl_load()) return 0;
+    int v = 0;
+    if (g_nccl.GetVersion(&v) != ncclSuccess) return 0;
+    return v;
+}
+
+int matinv_invert_sharded_f32(const float *A_host, int n, float *X_host, int *piv_host, int ngpu, int nb, int flags) {
+    if (n <= 0 || !A_host || !X_host) return shim_fail(MATINV_E_INVALID, "invalid argument");
+    if (nb != 0 && nb != MATINV_NB) return shim_fail(MATINV_E_UNSUPPORTED, "column blocks are %d wide (nb = 0 selects the default)", MATINV_NB);
+    if (flags & (MATINV_FLAG_TF32X3 | MATINV_FLAG_UNBLOCKED))
+        return shim_fail(MATINV_E_UNSUPPORTED, "the column-sharded path runs the bit-exact blocked FP32 schedule only");
+    const int rc = run_sharded(A_host, n, X_host, piv_host, ngpu, flags, 0ull, 0, true);
+    // the non-finite scan of the single-GPU extraction (SURVEY A.2 superset rule) on the assembled result
+    if (rc == MATINV_OK && !(flags & MATINV_FLAG_NOCHECK)) {
+        const size_t cnt = (size_t)n * n;
+        bool bad = false;
+        for (size_t k = 0; k < cnt && !bad; k++) bad = !std::isfinite(X_host[k]);
+        if (bad) return shim_fail(MATINV_SINGULAR, "singular: non-finite entry in the inverse");
+    }
+    return rc;
+}
+
+int matinv_sharded_synthetic_f32(int n, unsigned long long seed, int kind, int ngpu, int *piv_host, double *compute_ms) {
+    if (n <= 0) return shim_fail(MATINV_E_INVALID, "invalid argument");
+    const int rc = run_sharded(nullptr, n, nullptr, piv_host, ngpu, 0, seed, kind, true);
+    if (compute_ms) *compute_ms = g_last_sharded_ms;
+    return rc;
+}
+
+int matinv_invert_batched_f32_ngpu(const float *A_host, int n, long long batch, float *X_host, int *info_host, int ngpu, int flags) {
+    if (n <= 0 || n > 128 || batch < 0 || !A_host || !X_host) return shim_fail(MATINV_E_INVALID, "invalid argument (need 1 <= n <= 128)");
+    if (batch == 0) return MATINV_OK;
+    const int ndev = shim_device_count();
+    if (ndev == 0) return shim_fail(MATINV_E_NODEVICE, "no CUDA device");
+    if (ngpu <= 0) {
+        const char *e = getenv("MATINV_NGPU");
+        ngpu = e ? atoi(e) : ndev;
+        if (ngpu <= 0) ngpu = ndev;
+    }
+    if (ngpu > ndev) return shim_fail(MATINV_E_INVALID, "ngpu = %d but only %d CUDA device(s) are visible", ngpu, ndev);
+    if ((long long)ngpu > batch) ngpu = (int)batch;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    // contiguous index ranges [g * batch / G, (g+1) * batch / G): each GPU reads and writes only its slice
+    std::vector<int> rcs(ngpu, 0);
+    std::vector<std::string> errs(ngpu);
+    auto body = [&](int g) {
+        const long long b0 = batch * g / ngpu, b1 = batch * (g + 1) / ngpu, cnt = b1 - b0;
+        if (cnt <= 0) return;
+        cudaError_t e = cudaSetDevice(g);
+        float *dA = nullptr;
+        int *dI = nullptr;
+        cudaStream_t st = nullptr;
+        const size_t bytes = (size_t)cnt * n * n * sizeof(float);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&dA, bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&dI, (size_t)cnt * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dA, A_host + (size_t)b0 * n * n, bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_batched(dA, n, cnt, dA, dI, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(X_host + (size_t)b0 * n * n, dA, bytes, cudaMemcpyDeviceToHost, st);
+        std::vector<int> tmp;
+        int *ih = info_host ? info_host + b0 : nullptr;
+        if (!ih) { tmp.resize((size_t)cnt); ih = tmp.data(); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ih, dI, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, st);
+        const cudaError_t es = st ? cudaStreamSynchronize(st) : cudaSuccess;
+        if (e == cudaSuccess) e = es;
+        cudaFree(dA);
+        cudaFree(dI);
+        if (st) cudaStreamDestroy(st);
+        if (e != cudaSuccess) {
+            rcs[g] = MATINV_E_CUDA;
+            errs[g] = cudaGetErrorString(e);
+            return;
+        }
+        int any = 0;
+        for (long long b = 0; b < cnt; b++) any |= (ih[b] != 0);
+        rcs[g] = any ? MATINV_SINGULAR : MATINV_OK;
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < ngpu; g++) th.emplace_back(body, g);
+    body(0);
+    for (auto &t : th) t.join();
+    cudaSetDevice(cur);
+    int rc = MATINV_OK;
+    for (int g = 0; g < ngpu; g++) {
+        if (rcs[g] < 0) return shim_fail(rcs[g], "GPU %d: %s", g, errs[g].c_str());
+        if (rcs[g] == MATINV_SINGULAR) rc = MATINV_SINGULAR;
+    }
+    return rc;
+}
+
+}  // extern "C"

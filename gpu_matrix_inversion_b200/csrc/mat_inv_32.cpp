@@ -37,7 +37,13 @@ std::vector<float> matrix_inv_32(std::vector<float> matrix_vector, int matrix_or
     // reference's FMA chain) -- the signature clibgen binds cannot carry a flag, so the switch is an environment variable
     const char *tc = std::getenv("MATINV_TF32X3");
     if (tc && tc[0] && tc[0] != '0') flags |= MATINV_FLAG_TF32X3;
-    const int rc = matinv_invert_f32(matrix_vector.data(), matrix_order, result.data(), nullptr, flags);
+    // opt-in: MATINV_NGPU = k > 1 column-shards one inversion over k GPUs (bit-identical result; worth it from a few
+    // thousand rows up -- below that one GPU is faster and the single-device path is used)
+    const char *ng = std::getenv("MATINV_NGPU");
+    const int ngpu = ng ? std::atoi(ng) : 1;
+    const int rc = (ngpu > 1 && matrix_order >= 4096 && !(flags & MATINV_FLAG_TF32X3))
+                       ? matinv_invert_sharded_f32(matrix_vector.data(), matrix_order, result.data(), nullptr, ngpu, 0, flags & MATINV_FLAG_VERBOSE)
+                       : matinv_invert_f32(matrix_vector.data(), matrix_order, result.data(), nullptr, flags);
     if (rc == MATINV_OK) return result;
     if (rc < 0) std::cerr << "ERRORE N\xC2\xB0: " << rc << " (" << matinv_last_error() << ")" << std::endl;  // LIB:392
     return {};

@@ -575,6 +575,7 @@ int shim_fail(int code, const char *fmt, ...) {
     va_end(ap);
     return code;
 }
+void multi_shutdown();   // gj_multi.cu: NCCL communicators of the single-call multi-GPU entries
 int shim_device_count() {
     std::lock_guard<std::mutex> lk(g.mu);
     return probe_locked();
@@ -590,6 +591,7 @@ int matinv_device_count(void) {
 const char *matinv_last_error(void) { return g_err; }
 
 void matinv_shutdown(void) {
+    multi_shutdown();
     std::lock_guard<std::mutex> lk(g.mu);
     if (!g.probed || g.ndev == 0) return;
     int cur = 0;
@@ -719,8 +721,11 @@ int matinv_invert_batched_f32_dev(const float *A_dev, int n, long long batch, fl
 
 int matinv_invert_batched_f32(const float *A_host, int n, long long batch, float *X_host, int *info_host,
                               int flags) {
-    (void)flags;
     g_err[0] = 0;
+    {
+        const char *e = getenv("MATINV_NGPU");   // opt-in index split over several GPUs (gj_multi.cu)
+        if (e && atoi(e) > 1) return matinv_invert_batched_f32_ngpu(A_host, n, batch, X_host, info_host, atoi(e), flags);
+    }
     if (n <= 0 || n > 128 || batch < 0 || !A_host || !X_host) return fail(MATINV_E_INVALID, "invalid argument (need 1 <= n <= 128)");
     if (batch == 0) return MATINV_OK;
     std::lock_guard<std::mutex> lk(g.mu);

@@ -74,6 +74,26 @@ int matinv_invert_batched_f32(const float *A_host, int n, long long batch, float
 int matinv_invert_batched_f32_dev(const float *A_dev, int n, long long batch, float *X_dev, int *info_dev,
                                   void *stream, int flags);
 
+/* ---- single-call multi-GPU entries (one process, one host thread per GPU, NCCL) --------------
+ * SURVEY.md s.8(b)/(e).  The reference is single-device (LIB:239-250); these are what `matrix_inv_32` reaches when
+ * MATINV_NGPU > 1.  ngpu <= 0 selects MATINV_NGPU or, if unset, every visible device.
+ *
+ * matinv_invert_sharded_f32: one n x n matrix, columns dealt block-cyclically (blocks of 128, nb must be 0 or 128) to ngpu
+ * GPUs; per block step the owner factors the panel and ncclBroadcast ships pivots + multipliers; one grouped
+ * ncclSend/ncclRecv applies the deferred column permutation.  Result and pivot sequence are bit-identical to
+ * matinv_invert_f32.  Returns 0 / 1 (singular or non-finite) / < 0; MATINV_E_UNSUPPORTED when ngpu > 1 and NCCL cannot be
+ * loaded (libnccl.so.2 is opened with dlopen at first use). */
+int matinv_invert_sharded_f32(const float *A_host, int n, float *X_host, int *piv_host, int ngpu, int nb, int flags);
+/* Same schedule on the synthetic workload generated on the devices (no host matrix): timing aid for orders whose host
+ * copy would dominate.  compute_ms (may be NULL) = factorisation + column exchange on rank 0, CUDA events. */
+int matinv_sharded_synthetic_f32(int n, unsigned long long seed, int kind, int ngpu, int *piv_host, double *compute_ms);
+/* Batched small-n path split by matrix index over ngpu GPUs (contiguous index ranges, no communication).
+ * matinv_invert_batched_f32 takes this route when MATINV_NGPU > 1. */
+int matinv_invert_batched_f32_ngpu(const float *A_host, int n, long long batch, float *X_host, int *info_host, int ngpu,
+                                   int flags);
+/* NCCL version code of the library the multi-GPU entries would use (e.g. 22703), 0 if none can be loaded. */
+int matinv_nccl_version(void);
+
 /* ---- column-sharded single inversion: per-rank primitives, one process per GPU ---------------
  * The host (Python + torch.distributed, or any MPI-like launcher) owns the exchange step; these
  * calls own the math.  Columns are dealt block-cyclically in blocks of 128: global column block J
