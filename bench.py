@@ -407,6 +407,7 @@ def main():
         assert rc == m.OK
         e2e = {"value": world * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n,
                "d2h_bytes_per_step": 4 * n * n, "ms_per_step": e2e_s * 1e3,
+               "phases_s": m.last_phases(),   # last step: setup / H2D / factorisation / extraction + D2H / total (matinv_last_phases)
                "api": "matinv_invert_f32 (what matrix_inv_32 calls), pinned host buffers"}
 
         # optional 3xTF32 tcgen05 trailing update (north_star config 3: "FP32 SIMT vs 3xTF32 tcgen05"), same input, same K;
@@ -839,6 +840,7 @@ def main():
         assert rc == m.OK
         e2e = {"value": world * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n,
                "d2h_bytes_per_step": 4 * n * n, "ms_per_step": e2e_s * 1e3,
+               "phases_s": m.last_phases(),   # last step: setup / H2D / factorisation / extraction + D2H / total (matinv_last_phases)
                "api": "matinv_invert_f32 (what matrix_inv_32 calls), pinned host buffers"}
 
         # optional 3xTF32 tcgen05 trailing update (north_star config 3: "FP32 SIMT vs 3xTF32 tcgen05"), same input, same K;

@@ -42,7 +42,7 @@ EXPORTS = [
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
     "matinv_profile_read", "matinv_debug_trace", "matinv_invert_f64", "matinv_invert_f64_dev", "matinv_residual_f64_dev",
     "matinv_host_defect_f64", "matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev", "matinv_tf32x3_gate_dev", "matinv_invert_sharded_f32", "matinv_sharded_synthetic_f32",
-    "matinv_invert_batched_f32_ngpu", "matinv_nccl_version",
+    "matinv_invert_batched_f32_ngpu", "matinv_nccl_version", "matinv_last_phases",
 ]
 
 
@@ -75,6 +75,8 @@ def _load() -> ctypes.CDLL:
     L.matinv_residual_f64_dev.argtypes = [fp, fp, i, dp, vp]
     L.matinv_host_defect_f64.argtypes = [fp, fp, i, dp]
     L.matinv_last_timing.argtypes = [dp, dp]
+    L.matinv_last_phases.argtypes = [dp]
+    L.matinv_last_phases.restype = i
     L.matinv_ffma_peak_tflops.argtypes = [dp, vp]
     L.matinv_profile_enable.argtypes = [i]
     L.matinv_profile_enable.restype = None
@@ -138,6 +140,15 @@ def last_timing():
     if lib.matinv_last_timing(ctypes.byref(t), ctypes.byref(c)) != 0:
         return None
     return t.value, c.value
+
+
+def last_phases():
+    """Phase split of the last host-pointer inversion on this thread, like the reference's Res.times
+    (FP32_bench.cpp:256-443): dict(setup, h2d, factor, extract_d2h, total) in seconds, or None."""
+    out = (ctypes.c_double * 5)()
+    if lib.matinv_last_phases(out) != 0:
+        return None
+    return dict(zip(("setup", "h2d", "factor", "extract_d2h", "total"), (float(x) for x in out)))
 
 
 def _check(rc: int) -> int:

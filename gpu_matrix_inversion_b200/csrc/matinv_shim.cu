@@ -10,6 +10,7 @@
 //   LIB:369-381  getInvertedMatrix + enqueueReadBuffer -> extract_kernel + cudaMemcpyAsync
 // There is no CPU fallback: without a device every compute entry returns MATINV_E_NODEVICE.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -28,6 +29,15 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local double g_t_total = -1.0, g_t_compute = -1.0;
+// phases of the last host-pointer inversion on this thread, the split the reference's instrumented copy records
+// (SOL/FP32_bench.cpp:256-443, Res.times): setup, H2D, factorisation, extraction + D2H, total
+thread_local double g_phase[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
+
+// NVTX range for the lifetime of the object (shows up in Nsight Systems timelines; a no-op without a tool attached)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -109,6 +119,7 @@ struct DeviceCache {
     int *hostio_i = nullptr;
     size_t hostio_i_bytes = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h0 = nullptr, ev_f = nullptr;   // phase boundaries: before H2D, after the factorisation
     cudaStream_t copy_stream = nullptr;   // D2H of finished row chunks, overlapped with the extraction of the next chunk
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     cudaStream_t panel_stream = nullptr;  // high priority: the latency-critical panel kernels
@@ -173,6 +184,7 @@ void release_locked() {
     }
     if (G.stream) {
         cudaEventDestroy(G.ev[0]); cudaEventDestroy(G.ev[1]);
+        cudaEventDestroy(G.ev_h0); cudaEventDestroy(G.ev_f);
         cudaStreamDestroy(G.stream);
         G.stream = nullptr;
     }
@@ -227,6 +239,8 @@ int ensure_stream() {
         CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&G.ev[0]));
         CK(cudaEventCreate(&G.ev[1]));
+        CK(cudaEventCreate(&G.ev_h0));
+        CK(cudaEventCreate(&G.ev_f));
     }
     return 0;
 }
@@ -613,6 +627,7 @@ int matinv_invert_f32_dev(const float *A_dev, int n, float *X_dev, int *piv_dev,
     if (n <= 0 || !A_dev || !X_dev) return fail(MATINV_E_INVALID, "invalid argument");
     std::lock_guard<std::mutex> lk(g.mu);
     if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    NvtxRange whole("matinv_invert_f32_dev");
     return invert_dev_locked(A_dev, n, X_dev, piv_dev, (cudaStream_t)stream, flags);
 }
 
@@ -622,15 +637,23 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
     if (n <= 0 || !A_host || !X_host) return fail(MATINV_E_INVALID, "invalid argument");
     std::lock_guard<std::mutex> lk(g.mu);
     if (probe_locked() == 0) return fail(MATINV_E_NODEVICE, "no CUDA device");
+    NvtxRange whole("matinv_invert_f32");
+    for (double &p : g_phase) p = -1.0;
     const auto t0 = std::chrono::steady_clock::now();
+    nvtxRangePushA("setup: streams + staging");
     int rc = ensure_stream();
-    if (rc) return rc;
+    if (rc) { nvtxRangePop(); return rc; }
     const size_t bytes = (size_t)n * n * sizeof(float);
     rc = ensure_hostio(bytes, (size_t)n * sizeof(int));
+    nvtxRangePop();
     if (rc) return rc;
     cudaStream_t st = G.stream;
+    const double t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    nvtxRangePushA("H2D");
+    CK(cudaEventRecord(G.ev_h0, st));
     CK(cudaMemcpyAsync(G.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(G.ev[0], st));
+    nvtxRangePop();
     if (flags & MATINV_FLAG_TF32X3) {
         // gated tensor-core path: A stays in hostio while X is written to a second buffer, then one D2H copy
         if (G.hostx_bytes < bytes) {
@@ -656,8 +679,12 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
         }
         return rc;
     }
+    nvtxRangePushA("factorisation (enqueue)");
     rc = factor_locked(G.hostio, n, st, flags);
+    nvtxRangePop();
     if (rc) return rc;
+    CK(cudaEventRecord(G.ev_f, st));
+    NvtxRange tail("extraction + D2H");
     // extraction (deferred column permutation + isfinite scan) in row chunks, each chunk's D2H copy overlapped with the
     // extraction of the next one on a second stream -- replaces getInvertedMatrix + enqueueReadBuffer (LIB:369-381)
     rc = ensure_copy_stream();
@@ -698,6 +725,16 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
     CK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]));
     g_t_compute = ms * 1e-3;
     g_t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    {
+        float h2d = 0.f, fac = 0.f;
+        if (cudaEventElapsedTime(&h2d, G.ev_h0, G.ev[0]) == cudaSuccess && cudaEventElapsedTime(&fac, G.ev[0], G.ev_f) == cudaSuccess) {
+            g_phase[0] = t_setup;
+            g_phase[1] = h2d * 1e-3;
+            g_phase[2] = fac * 1e-3;
+            g_phase[3] = g_t_total - t_setup - (h2d + fac) * 1e-3;   // extraction with its overlapped D2H, status read-back
+            g_phase[4] = g_t_total;
+        }
+    }
     if (flags & MATINV_FLAG_VERBOSE) {  // the reference's two stdout lines (LIB:385-386)
         printf("Tempo Totale Impiegato: %g seconds\n", g_t_total);
         printf("Tempo Computazione: %g seconds\n", g_t_compute);
@@ -877,6 +914,12 @@ int matinv_host_defect_f64(const double *A_host, const double *B_host, int n, do
     cudaFree(dB);
     if (e != cudaSuccess) return fail(MATINV_E_CUDA, "%s", cudaGetErrorString(e));
     return MATINV_OK;
+}
+
+int matinv_last_phases(double *out5) {
+    if (!out5 || g_phase[4] < 0) return 1;
+    for (int i = 0; i < 5; i++) out5[i] = g_phase[i];
+    return 0;
 }
 
 int matinv_last_timing(double *total_s, double *compute_s) {

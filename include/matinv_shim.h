@@ -151,6 +151,12 @@ int matinv_host_defect_f64(const double *A_host, const double *B_host, int n, do
  * reference's "Tempo Totale") and compute ("Tempo Computazione").  Returns 0 if available. */
 int matinv_last_timing(double *total_s, double *compute_s);
 
+/* Phase split of the last matinv_invert_f32 on this thread, the phases the reference's instrumented copy records
+ * (SOL/FP32_bench.cpp:256-443, Res.times): out5 = {setup (streams / staging buffers), H2D, factorisation, extraction + D2H
+ * (overlapped) + status read-back, total}, seconds; device phases from CUDA events.  The same phases are NVTX ranges
+ * ("matinv_invert_f32", "H2D", ...) for Nsight Systems.  Returns 0 if available (not for MATINV_FLAG_TF32X3 calls). */
+int matinv_last_phases(double *out5);
+
 /* Profiling hooks for bench.py.  With profiling enabled the shim brackets every trailing-update
  * (GEMM) launch with CUDA events on the launching stream.  matinv_profile_read returns, for the
  * calls made since the last matinv_profile_enable: summed GEMM time (ms), number of GEMM launches,

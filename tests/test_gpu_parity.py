@@ -435,3 +435,17 @@ def test_large_order_shapes_property(m):
         out.append((line[1], float(line[2])))
     assert out[0][0] == out[1][0], out
     assert out[0][1] <= 1e-5 and out[1][1] <= 1e-5, out
+
+
+def test_phase_timers(m):
+    """matinv_last_phases: the reference's instrumented copy reports per-phase times (FP32_bench.cpp:256-443); here setup /
+    H2D / factorisation / extraction + D2H / total of the last host-pointer call."""
+    A = o.uniform(1500)
+    X = m.invert(A)
+    assert X is not None
+    ph = m.last_phases()
+    assert ph is not None and all(v >= 0.0 for v in ph.values()), ph
+    assert abs(ph["setup"] + ph["h2d"] + ph["factor"] + ph["extract_d2h"] - ph["total"]) <= 1e-6 * max(1.0, ph["total"]) + 1e-9
+    assert ph["factor"] > 0.0 and ph["total"] >= ph["factor"]
+    t = m.last_timing()
+    assert t is not None and abs(t[0] - ph["total"]) < 1e-9
