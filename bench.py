@@ -650,466 +650,6 @@ def main():
                   "exchange": "NCCL broadcast of the factored panel per block step + one all-to-all for the column permutation"}
         unit, scaling = "GFLOP/s", "strong"
 
-    line = {"metric": METRIC, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64" if args.workload != "batched64" else "f32", "data": "synthetic",
-            "impl": "reference",
-            "config": {"workload": (f"batched {1 << 20} x 64x64 FP32 inversions per GPU, split by matrix index" if args.workload == "batched64"
-                                    else f"N={n_target} random-{args.kind} FP32 single inversion per GPU, partial pivoting"),
-                       "n": n_target, "same_order_as_metric": bool(args.workload != "batched64" and K == n_target),
-                       "sample": sample},
-            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": REF_KIND, "sample": sample},
-            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
-
-
-# ----------------------------------------------------------------------------- column-sharded run (torchrun ranks)
-
-def run_sharded_workload(m, torch, dist, n, kind, seed, K, W, rank, world, local, check_single_gpu):
-    """K timed column-sharded inversions of one n x n matrix over all ranks (owner factors -> NCCL broadcast -> all apply;
-    one all-to-all for the deferred column permutation), CUDA events, max over ranks.  With check_single_gpu every rank
-    then inverts the SAME matrix alone on its own GPU (the 1-GPU base of the strong-scaling figure, timed in this job) and
-    compares its column blocks of the sharded result and the pivot sequence bit for bit; the O(n^2) probe gives the
-    residual.  Raises on a mismatch."""
-    from gpu_matrix_inversion_b200.sharded import BLOCK, CudaShardBackend, ShardedInverter
-
-    dev = torch.device("cuda", local)
-    backend = CudaShardBackend(n, rank, world, dev)
-    inv = ShardedInverter(backend, dist if world > 1 else None)
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def one_step():
-        backend.generate(seed, kind)      # the factorisation is in place: regenerate (cheap, on device)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if world > 1:
-            dist.barrier()
-        e0.record()
-        info, piv = inv.factorize()
-        out = inv.exchange_columns(piv)
-        e1.record()
-        torch.cuda.synchronize()
-        assert info == 0
-        return e0.elapsed_time(e1), piv, out
-
-    for _ in range(W):
-        one_step()
-    times = []
-    for _ in range(K):
-        t, piv, out = one_step()
-        times.append(t)
-    ms = max_over_ranks(sum(times) / len(times))
-    res = {"n": n, "ms_per_step": ms, "value": 2.0 * n ** 3 / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "steps": K, "warmup": W,
-           "n_gpus": world, "scaling": "strong",
-           "comm": {"collective": "ncclBroadcast (torch.distributed, high-priority stream) of the factored panel per 128-column block"
-                                  " + one all_to_all for the deferred column permutation",
-                    "bytes_per_block_step": backend.msg_bytes, "block_steps": (n + BLOCK - 1) // BLOCK,
-                    "all_to_all_bytes_per_rank": 4 * n * len(backend.blocks) * BLOCK}}
-    if check_single_gpu:
-        A = m.generate_dev(n, seed, kind)
-        Xs = torch.empty_like(A)
-        pivs = torch.empty(n, dtype=torch.int32, device="cuda")
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        rc, _ = m.invert_dev(A, Xs, piv=pivs)          # untimed: sizes the workspace for this order
-        assert rc == m.OK, m.last_error()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        e0.record()
-        rc, _ = m.invert_dev(A, Xs, piv=pivs)
-        e1.record()
-        torch.cuda.synchronize()
-        assert rc == m.OK, m.last_error()
-        ms1 = max_over_ranks(e0.elapsed_time(e1))
-        same = bool(torch.equal(pivs.cpu(), torch.from_numpy(piv)))
-        for J, blk in out.items():
-            same = same and bool(torch.equal(blk.contiguous().view(torch.int32), Xs[:, J * BLOCK:J * BLOCK + blk.shape[1]].contiguous().view(torch.int32)))
-        flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        same_all = bool(flag.item() == 1.0)
-        est = m.probe_residual_dev(A, Xs)
-        res.update({"t_1gpu_ms": ms1, "speedup_vs_1gpu": ms1 / ms, "bitwise_equal_single_gpu": same_all, "residual": est,
-                    "residual_note": "O(n^2) randomised estimate of ||AX-I||_F/(n||A||_F||X||_F) on the single-GPU inverse every "
-                                     "rank computed in this job; the sharded result's column blocks and pivot sequence equal it "
-                                     "bit for bit on every rank, so it is the sharded result's residual too",
-                    "t_1gpu_note": "same matrix inverted alone on every GPU (max over ranks), timed in this job"})
-        del A, Xs
-        if not same_all:
-            raise SystemExit(f"sharded N={n}: result differs from the single-GPU result (rank {rank})")
-        if not (est <= 1e-5):
-            raise SystemExit(f"sharded N={n}: residual estimate {est} above 1e-5")
-    del out
-    backend.close()
-    torch.cuda.empty_cache()
-    return res
-
-
-# ----------------------------------------------------------------------------- our arm
-
-def main():
-    args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-        return
-
-    import torch
-    import torch.distributed as dist
-
-    import gpu_matrix_inversion_b200 as m
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available() or m.device_count() == 0:
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # high-priority NCCL streams: with look-ahead the panel broadcast must not queue behind the trailing GEMM
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    from oracle.gj_oracle import SEED_BATCHED, SEED_DIAGDOM, SEED_UNIFORM  # constants only
-
-    sampler = ClockSampler(local)
-    K, W = args.steps, max(args.warmup, 0)
-    extra = {}
-
-    if args.workload in ("n16384", "n4096", "n32768"):
-        n = {"n16384": 16384, "n4096": 4096, "n32768": 32768}[args.workload]
-        seed = (SEED_UNIFORM if args.kind == "uniform" else SEED_DIAGDOM) + n + rank * 7919
-        A = m.generate_dev(n, seed, args.kind)
-        X = torch.empty_like(A)
-        for _ in range(W):
-            rc, _ = m.invert_dev(A, X)
-            assert rc == m.OK, m.last_error()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m.profile_enable(True)
-        barrier()
-        sampler.start()
-        ev0.record()
-        for _ in range(K):
-            rc, _ = m.invert_dev(A, X)
-        ev1.record()
-        torch.cuda.synchronize()
-        clocks = sampler.stop()
-        barrier()
-        prof = m.profile_read()
-        m.profile_enable(False)
-        assert rc == m.OK
-        ms = max_over_ranks(ev0.elapsed_time(ev1) / K)
-        flops = 2.0 * n ** 3
-        value = world * flops / (ms * 1e-3) / 1e9
-        res, _ = m.residual_dev(A, X) if n <= 16384 else (None, None)
-        extra["residual"] = res
-
-        # e2e: same metric through the host-pointer C-ABI entry, pinned host buffers, H2D + D2H inside
-        Ah = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
-        Xh = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
-        Ah.copy_(A)
-        torch.cuda.synchronize()
-        for _ in range(1):
-            rc = m.lib.matinv_invert_f32(Ah.data_ptr(), n, Xh.data_ptr(), None, 0)
-            assert rc == m.OK, m.last_error()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            rc = m.lib.matinv_invert_f32(Ah.data_ptr(), n, Xh.data_ptr(), None, 0)
-        torch.cuda.synchronize()
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / K)
-        assert rc == m.OK
-        e2e = {"value": world * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n,
-               "d2h_bytes_per_step": 4 * n * n, "ms_per_step": e2e_s * 1e3,
-               "phases_s": m.last_phases(),   # last step: setup / H2D / factorisation / extraction + D2H / total (matinv_last_phases)
-               "api": "matinv_invert_f32 (what matrix_inv_32 calls), pinned host buffers"}
-
-        # optional 3xTF32 tcgen05 trailing update (north_star config 3: "FP32 SIMT vs 3xTF32 tcgen05"), same input, same K;
-        # the residual gate (O(N^2) probe + status read-back) is inside the timed region.  Its dominant kernel is HBM-bound.
-        for _ in range(2):
-            rc, _ = m.invert_dev(A, X, flags=m.FLAG_TF32X3)
-            assert rc == m.OK, m.last_error()
-        m.profile_enable(True)
-        barrier()
-        ev0.record()
-        for _ in range(K):
-            rc, _ = m.invert_dev(A, X, flags=m.FLAG_TF32X3)
-        ev1.record()
-        torch.cuda.synchronize()
-        barrier()
-        prof_tc = m.profile_read()
-        m.profile_enable(False)
-        st_tc = m.tf32x3_status()
-        ms_tc = max_over_ranks(ev0.elapsed_time(ev1) / K)
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        tc_ms = prof_tc["gemm_ms"] / max(prof_tc["gemm_launches"], 1)
-        tc_bytes = prof_tc["gemm_flops"] / max(prof_tc["gemm_launches"], 1) / 32.0   # 8 B (read + write) per 2*128 flops
-        tc_gbs = tc_bytes / (tc_ms * 1e-3) / 1e9 if tc_ms else 0.0
-        tc_traffic = None
-        ttf = ROOT / "profiles" / "r01_tf32x3_traffic.json"
-        if n == 16384 and ttf.exists():   # DRAM bytes of one strip-kernel launch, from the committed ncu --set full capture
-            tc_traffic = json.loads(ttf.read_text())["dram_bytes_total"]
-        extra["tf32x3"] = {
-            "value": world * flops / (ms_tc * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_tc,
-            "speedup_vs_fp32_simt": ms / ms_tc, "residual_estimate": st_tc["estimate"], "fell_back": st_tc["fell_back"],
-            "residual": m.residual_dev(A, X)[0] if n <= 16384 else None, "gate": m.TF32X3_GATE,
-            "gpu_launches": prof_tc["launches"],
-            "roofline": {"bound": "hbm", "kernel": "tf32_split_kernel + trailing_tf32x3_strip_kernel (tcgen05.mma kind::tf32, TMEM)",
-                         "achieved": tc_gbs, "peak": hbm, "unit": "GB/s", "frac": tc_gbs / hbm, "traffic": tc_traffic,
-                         "traffic_note": "static: DRAM bytes per launch from the committed round-1 ncu --set full capture (profiles/r01_tf32x3_traffic.json), not re-measured in this run",
-                         "algorithmic_bytes_per_launch": tc_bytes, "ms_per_launch": tc_ms,
-                         "tensor_tflops_3x": 3.0 * prof_tc["gemm_flops"] / max(prof_tc["gemm_launches"], 1) / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                         "kernel_share_of_step": prof_tc["gemm_ms"] / K / ms_tc},
-            "note": "not bit-identical to the reference's FMA chain: accepted per inversion by the residual gate, else the "
-                    "FP32 SIMT schedule is rerun (fell_back)"}
-
-        peak = m.ffma_peak_tflops()
-        gemm_ms = prof["gemm_ms"] / max(prof["gemm_launches"], 1)
-        gemm_tflops = prof["gemm_flops"] / max(prof["gemm_launches"], 1) / (gemm_ms * 1e-3) / 1e12 if gemm_ms else 0.0
-        traffic = None
-        tf = ROOT / "profiles" / "r01_gemm_traffic.json"
-        if n == 16384 and tf.exists():   # DRAM bytes of one trailing-update launch, from the committed ncu --set full capture
-            traffic = json.loads(tf.read_text())["dram_bytes_total"]
-        roofline = {"bound": "fp32_simt", "kernel": "trailing_gemm_kernel", "achieved": gemm_tflops, "peak": peak,
-                    "unit": "TFLOP/s", "frac": gemm_tflops / peak if peak else None, "traffic": traffic,
-                    "traffic_note": "static: DRAM bytes per launch from the committed round-1 ncu --set full capture (profiles/r01_gemm_traffic.json), not re-measured in this run; algorithmic bytes 2.098e9",
-                    "peak_source": "measured live: matinv_ffma_peak_tflops (FFMA register-tile probe); "
-                                   "MEASURED_PEAKS.json has no FP32 SIMT entry",
-                    "kernel_share_of_step": prof["gemm_ms"] / K / ms,
-                    "whole_inversion_frac_of_peak": (flops / (ms * 1e-3) / 1e12) / peak if peak else None,
-                    "nominal_fp32_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}
-        launches = prof["launches"]
-        if args.workload == "n16384" and not args.no_extras:
-            # ---- BASELINE config 4 on the same line: 2^20 x 64x64 per GPU, split by index (no collective)
-            del Ah, Xh
-            bn, bb = 64, args.batch
-            Ab = m.generate_batched_dev(bn, rank * bb, bb, SEED_BATCHED)
-            Xb = torch.empty_like(Ab)
-            ib = torch.empty(bb, dtype=torch.int32, device="cuda")
-            for _ in range(2):
-                m.invert_batched_dev(Ab, Xb, ib)
-            barrier()
-            bK = max(3, min(K, 10))
-            ev0.record()
-            for _ in range(bK):
-                m.invert_batched_dev(Ab, Xb, ib)
-            ev1.record()
-            torch.cuda.synchronize()
-            assert int((ib != 0).sum()) == 0
-            bms = max_over_ranks(ev0.elapsed_time(ev1) / bK)
-            gbs = bb * 2 * bn * bn * 4 / (bms * 1e-3) / 1e9
-            extra["batched64"] = {
-                "value": world * bb / (bms * 1e-3), "unit": "inv/s", "ms_per_step": bms, "steps": bK, "batch_per_gpu": bb, "n": bn,
-                "scaling": "weak", "parallelism": f"index_split_x{world}",
-                "roofline": {"bound": "hbm", "kernel": "batched_pk_kernel (one warp per matrix, register resident)", "achieved": gbs,
-                             "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
-                             "algorithmic_bytes_per_matrix": 2 * bn * bn * 4,
-                             "fp32_frac": (bb * 2.0 * bn ** 3 / (bms * 1e-3) / 1e12) / peak if peak else None, "fp32_peak_tflops": peak,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                             "note": "AI = 16 flop/B sits above the FP32 ridge: the FP32-bound ceiling is ~72 % of HBM peak (SURVEY Appendix C)"}}
-            launches += bK
-            del Ab, Xb, ib
-            torch.cuda.empty_cache()
-            if world > 1:
-                # ---- BASELINE config 5 on the same line: one N=65536 matrix column-sharded over all ranks (strong scaling)
-                del A, X
-                torch.cuda.empty_cache()
-                ns = args.sharded_order
-                extra["sharded_n%d" % ns] = run_sharded_workload(m, torch, dist, ns, args.kind, (SEED_UNIFORM if args.kind == "uniform" else SEED_DIAGDOM) + ns,
-                                                                  2, 1, rank, world, local, check_single_gpu=True)
-        config = {"workload": f"N={n} random-{args.kind} FP32 single inversion per GPU, partial pivoting",
-                  "n": n, "nb": 128, "l2": "inputs_larger_than_l2" if n >= 8192 else "l2_resident_input",
-                  "parallelism": f"replicas_x{world}" if world > 1 else "single_gpu"}
-        unit, scaling = "GFLOP/s", "weak"
-    elif args.workload == "fp64_n4096":
-        # FP64 entry point (matrix_inversion_FP64), blocked schedule of gj_f64.cu
-        n = 4096
-        gen = torch.Generator(device="cuda").manual_seed(0xB2006400 + rank)
-        A = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=gen) * 100.0
-        X = torch.empty_like(A)
-        for _ in range(W):
-            rc, _ = m.invert_f64_dev(A, X)
-            assert rc == m.OK, m.last_error()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        sampler.start()
-        ev0.record()
-        for _ in range(K):
-            rc, _ = m.invert_f64_dev(A, X)
-        ev1.record()
-        torch.cuda.synchronize()
-        clocks = sampler.stop()
-        barrier()
-        assert rc == m.OK
-        # kernel-level pass: one more inversion with an event pair around each trailing update
-        m.profile_enable(True)
-        rc, _ = m.invert_f64_dev(A, X)
-        torch.cuda.synchronize()
-        prof = m.profile_read()
-        m.profile_enable(False)
-        ms = max_over_ranks(ev0.elapsed_time(ev1) / K)
-        flops = 2.0 * n ** 3
-        value = world * flops / (ms * 1e-3) / 1e9
-        R = A @ X - torch.eye(n, dtype=torch.float64, device="cuda")
-        extra["residual"] = float(R.norm() / (n * A.norm() * X.norm()))
-        Ah = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
-        Xh = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
-        Ah.copy_(A)
-        torch.cuda.synchronize()
-        rc = m.lib.matinv_invert_f64(Ah.data_ptr(), n, Xh.data_ptr(), None, 0)
-        assert rc == m.OK, m.last_error()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            rc = m.lib.matinv_invert_f64(Ah.data_ptr(), n, Xh.data_ptr(), None, 0)
-        torch.cuda.synchronize()
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / K)
-        e2e = {"value": world * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n * n,
-               "d2h_bytes_per_step": 8 * n * n, "ms_per_step": e2e_s * 1e3,
-               "api": "matinv_invert_f64 (what matrix_inversion_FP64 calls), pinned host buffers"}
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        # the hooks bracket the trailing updates of the blocked schedule: per launch (n-64)^2 doubles read + written and
-        # 2 (n-64)^2 64 flop; both ceilings are reported because at 64-wide panels the kernel sits near the ridge
-        k_ms = prof["gemm_ms"] / max(prof["gemm_launches"], 1)
-        mrows = float(n - 64)
-        gbs = 16.0 * mrows * mrows / (k_ms * 1e-3) / 1e9 if k_ms else 0.0
-        tfl = 2.0 * mrows * mrows * 64 / (k_ms * 1e-3) / 1e12 if k_ms else 0.0
-        fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12
-        roofline = {"bound": "hbm", "kernel": "trailing_f64_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s",
-                    "frac": gbs / hbm, "traffic": None,
-                    "traffic_note": "algorithmic bytes per launch 16 (n-64)^2 = 2.60e8 (the 134 MB matrix is about the size of "
-                                    "L2, so part of it is served from L2 at this order)",
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                    "fp64_tflops": tfl, "fp64_frac_of_nominal": tfl / fp64_nominal, "fp64_nominal_peak_tflops": fp64_nominal,
-                    "kernel_share_of_step": prof["gemm_ms"] / ms}
-        launches = prof["launches"] * K
-        config = {"workload": f"N={n} U(0,100) FP64 single inversion per GPU, partial pivoting (matrix_inversion_FP64)",
-                  "n": n, "l2": "input_about_l2_size", "parallelism": f"replicas_x{world}" if world > 1 else "single_gpu",
-                  "path": "blocked, 64-column panels (two launches per column + recurrence + trailing update per panel)"}
-        unit, scaling = "GFLOP/s", "weak"
-    elif args.workload == "batched64":
-        n, batch = 64, args.batch
-        A = m.generate_batched_dev(n, rank * batch, batch, SEED_BATCHED)
-        X = torch.empty_like(A)
-        info = torch.empty(batch, dtype=torch.int32, device="cuda")
-        for _ in range(W):
-            m.invert_batched_dev(A, X, info)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m.profile_enable(True)
-        barrier()
-        sampler.start()
-        ev0.record()
-        for _ in range(K):
-            m.invert_batched_dev(A, X, info)
-        ev1.record()
-        torch.cuda.synchronize()
-        clocks = sampler.stop()
-        barrier()
-        launches = m.profile_read()["launches"]
-        m.profile_enable(False)
-        assert int((info != 0).sum()) == 0
-        ms = max_over_ranks(ev0.elapsed_time(ev1) / K)
-        value = world * batch / (ms * 1e-3)
-        nb_e2e = min(batch, 1 << 17)
-        Ah = torch.empty((nb_e2e, n, n), dtype=torch.float32, pin_memory=True)
-        Xh = torch.empty_like(Ah).pin_memory()
-        Ah.copy_(A[:nb_e2e])
-        ih = torch.empty(nb_e2e, dtype=torch.int32)
-        m.lib.matinv_invert_batched_f32(Ah.data_ptr(), n, nb_e2e, Xh.data_ptr(), ih.data_ptr(), 0)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            m.lib.matinv_invert_batched_f32(Ah.data_ptr(), n, nb_e2e, Xh.data_ptr(), ih.data_ptr(), 0)
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / K)
-        e2e = {"value": world * nb_e2e / e2e_s, "unit": "inv/s", "h2d_bytes_per_step": 4 * n * n * nb_e2e,
-               "d2h_bytes_per_step": 4 * n * n * nb_e2e + 4 * nb_e2e, "batch": nb_e2e}
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        gbs = batch * 2 * n * n * 4 / (ms * 1e-3) / 1e9
-        peak32 = m.ffma_peak_tflops()
-        roofline = {"bound": "hbm", "kernel": "batched kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s",
-                    "frac": gbs / hbm, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                    "fp32_frac": (batch * 2.0 * n ** 3 / (ms * 1e-3) / 1e12) / peak32 if peak32 else None,
-                    "fp32_peak_tflops": peak32}
-        config = {"workload": f"batched {batch} x 64x64 FP32 inversions per GPU, split by matrix index", "n": 64,
-                  "batch_per_gpu": batch, "l2": "inputs_larger_than_l2", "parallelism": f"index_split_x{world}"}
-        unit, scaling = "inv/s", "weak"
-    else:
-        # ---- one matrix column-sharded over the ranks (strong scaling): owner factors -> NCCL broadcast -> all apply
-        from gpu_matrix_inversion_b200.sharded import CudaShardBackend, ShardedInverter
-
-        n = args.order or 65536
-        dev = torch.device("cuda", local)
-        backend = CudaShardBackend(n, rank, world, dev)
-        inv = ShardedInverter(backend, dist if world > 1 else None)
-        seed = (SEED_UNIFORM if args.kind == "uniform" else SEED_DIAGDOM) + n
-
-        def one_step():
-            backend.generate(seed, args.kind)      # the factorisation is in place: regenerate (cheap, on device)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if world > 1:
-                dist.barrier()
-            e0.record()
-            info, piv = inv.factorize()
-            out = inv.exchange_columns(piv)
-            e1.record()
-            torch.cuda.synchronize()
-            assert info == 0
-            return e0.elapsed_time(e1), out
-
-        for _ in range(min(W, 1)):
-            one_step()
-        barrier()
-        sampler.start()
-        times = []
-        for _ in range(K):
-            t, out = one_step()
-            times.append(t)
-        clocks = sampler.stop()
-        barrier()
-        del out
-        ms = max_over_ranks(sum(times) / len(times))
-        flops = 2.0 * n ** 3
-        value = flops / (ms * 1e-3) / 1e9
-        peak = m.ffma_peak_tflops()
-        nblk = (n + 127) // 128
-        launches = (nblk // max(world, 1)) * 16 + nblk * 4
-        e2e = {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * n + 4,
-               "note": "input generated on the device (16 GiB at N=65536 does not round-trip the host); "
-                       "status word + pivots are read back every step"}
-        roofline = {"bound": "fp32_simt", "kernel": "trailing_gemm_kernel", "achieved": value / 1e3 / world, "peak": peak,
-                    "unit": "TFLOP/s", "frac": value / 1e3 / world / peak if peak else None, "traffic": None,
-                    "peak_source": "measured live: matinv_ffma_peak_tflops; achieved = whole-job rate per GPU"}
-        config = {"workload": f"N={n} random-{args.kind} FP32 single inversion, 1-D block-cyclic column sharding (128)",
-                  "n": n, "nb": 128, "l2": "inputs_larger_than_l2", "parallelism": f"column_shards_x{world}",
-                  "exchange": "NCCL broadcast of the factored panel per block step + one all-to-all for the column permutation"}
-        unit, scaling = "GFLOP/s", "strong"
-        backend.close()
-
     line = {"metric": METRIC, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64" if args.workload == "fp64_n4096" else "f32",

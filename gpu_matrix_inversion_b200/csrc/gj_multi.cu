@@ -279,8 +279,26 @@ void rank_factor(int g, Shared &sh, RankState &S) {
     RCK(cudaStreamSynchronize(S.main));
 }
 
+// MATINV_MULTI_TRACE=1: per rank, CUDA events on the main stream around the point where it waits for the side stream
+// (next panel's message): "busy" = time the main stream spends in its own kernels, "stall" = time it waits for the
+// message of the next panel.  Printed to stderr; diagnostic only.
+bool multi_trace() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("MATINV_MULTI_TRACE");
+        on = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 void rank_schedule(int g, Shared &sh, RankState &S) {
     const int G = sh.ngpu, nblk = sh.nblk;
+    const bool trace = multi_trace();
+    std::vector<cudaEvent_t> ea, eb;
+    if (trace) {
+        ea.resize(nblk); eb.resize(nblk);
+        for (int J = 0; J < nblk; J++) { cudaEventCreate(&ea[J]); cudaEventCreate(&eb[J]); }
+    }
     ncclComm_t comm = (G > 1) ? g_comms.comm[g] : nullptr;
     const size_t mbytes = (size_t)matinv_shard_panel_bytes(sh.n);
     RCK(cudaSetDevice(g));
@@ -310,9 +328,25 @@ void rank_schedule(int g, Shared &sh, RankState &S) {
             RMK(matinv_shard_apply(S.sh, J, msg, S.main));
         }
         RCK(cudaEventRecord(S.ev_done, S.side));
+        if (trace) cudaEventRecord(ea[J], S.main);
         RCK(cudaStreamWaitEvent(S.main, S.ev_done, 0));
+        if (trace) cudaEventRecord(eb[J], S.main);
     }
     RCK(cudaEventRecord(S.ev_t1, S.main));
+    if (trace) {
+        cudaStreamSynchronize(S.main);
+        double busy = 0.0, stall = 0.0, stall_owner = 0.0;
+        float ms = 0.f;
+        for (int J = 0; J + 1 < nblk; J++) {
+            if (cudaEventElapsedTime(&ms, ea[J], eb[J]) == cudaSuccess) { stall += ms; if (owner_of(J + 1, G) == g) stall_owner += ms; }
+            if (J > 0 && cudaEventElapsedTime(&ms, eb[J - 1], ea[J]) == cudaSuccess) busy += ms;
+        }
+        float tot = 0.f;
+        cudaEventElapsedTime(&tot, S.ev_t0, S.ev_t1);
+        fprintf(stderr, "[matinv multi trace] rank %d/%d: total %.1f ms, main stream busy %.1f ms, waiting for the next panel's message %.1f ms (%.1f ms of it in steps where this rank factors)\n",
+                g, G, tot, busy, stall, stall_owner);
+        for (int J = 0; J < nblk; J++) { cudaEventDestroy(ea[J]); cudaEventDestroy(eb[J]); }
+    }
 }
 
 void rank_status(int g, Shared &sh, RankState &S, std::vector<int> &piv, int &info) {
