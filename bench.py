@@ -233,6 +233,30 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- column-sharded run (torchrun ranks)
 
+_BCAST_GROUP = None   # (group,) once created
+
+
+def make_bcast_group(dist, world):
+    """NCCL process group for the per-block panel broadcasts, limited to MATINV_SHARD_BCAST_CTAS (default 2) CTAs and on a
+    high-priority stream.  A receiver posts the broadcast of panel J+1 a whole block step ahead and its kernel spins until
+    the owner has factored the panel: every CTA it holds is an SM slot the trailing GEMM does not get (measured with the
+    C-ABI driver on 8 GPUs, N=65536: 1474.6 ms of main-stream work with NCCL's default channel count, 1420.7 ms with 2;
+    the exchange is hidden behind the GEMM either way, so its own speed does not matter)."""
+    if world <= 1:
+        return None
+    ctas = int(os.environ.get("MATINV_SHARD_BCAST_CTAS", "2"))
+    if ctas <= 0:
+        return None
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        opts.config.min_ctas = 1
+        opts.config.max_ctas = ctas
+        return dist.new_group(ranks=list(range(world)), pg_options=opts)
+    except Exception:
+        return None
+
+
 def run_sharded_workload(m, torch, dist, n, kind, seed, K, W, rank, world, local, check_single_gpu):
     """K timed column-sharded inversions of one n x n matrix over all ranks (owner factors -> NCCL broadcast -> all apply;
     one all-to-all for the deferred column permutation), CUDA events, max over ranks.  With check_single_gpu every rank
@@ -243,7 +267,11 @@ def run_sharded_workload(m, torch, dist, n, kind, seed, K, W, rank, world, local
 
     dev = torch.device("cuda", local)
     backend = CudaShardBackend(n, rank, world, dev)
-    inv = ShardedInverter(backend, dist if world > 1 else None)
+    global _BCAST_GROUP
+    if world > 1 and _BCAST_GROUP is None:
+        _BCAST_GROUP = (make_bcast_group(dist, world),)
+    bgroup = _BCAST_GROUP[0] if _BCAST_GROUP else None
+    inv = ShardedInverter(backend, dist if world > 1 else None, bcast_group=bgroup)
 
     def max_over_ranks(x):
         if world == 1:
@@ -275,8 +303,9 @@ def run_sharded_workload(m, torch, dist, n, kind, seed, K, W, rank, world, local
     ms = max_over_ranks(sum(times) / len(times))
     res = {"n": n, "ms_per_step": ms, "value": 2.0 * n ** 3 / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "steps": K, "warmup": W,
            "n_gpus": world, "scaling": "strong",
-           "comm": {"collective": "ncclBroadcast (torch.distributed, high-priority stream) of the factored panel per 128-column block"
-                                  " + one all_to_all for the deferred column permutation",
+           "comm": {"collective": "ncclBroadcast (torch.distributed, high-priority stream"
+                                  + (", process group limited to %s CTAs" % os.environ.get("MATINV_SHARD_BCAST_CTAS", "2") if bgroup is not None else "")
+                                  + ") of the factored panel per 128-column block + one all_to_all for the deferred column permutation",
                     "bytes_per_block_step": backend.msg_bytes, "block_steps": (n + BLOCK - 1) // BLOCK,
                     "all_to_all_bytes_per_rank": 4 * n * len(backend.blocks) * BLOCK}}
     if check_single_gpu:

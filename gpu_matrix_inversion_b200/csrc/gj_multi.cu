@@ -49,6 +49,8 @@ struct Nccl {
     void *h = nullptr;
     bool tried = false;
     decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommInitRankConfig) CommInitRankConfig = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclCommAbort) CommAbort = nullptr;
     decltype(&ncclBroadcast) Broadcast = nullptr;
@@ -74,6 +76,8 @@ bool nccl_load() {
     g_nccl.field = (decltype(g_nccl.field))dlsym(h, #name);     \
     if (!g_nccl.field) { dlclose(h); return false; }
     NCCL_SYM(CommInitAll, ncclCommInitAll)
+    NCCL_SYM(CommInitRankConfig, ncclCommInitRankConfig)
+    NCCL_SYM(GetUniqueId, ncclGetUniqueId)
     NCCL_SYM(CommDestroy, ncclCommDestroy)
     NCCL_SYM(CommAbort, ncclCommAbort)
     NCCL_SYM(Broadcast, ncclBroadcast)
@@ -140,31 +144,68 @@ void column_gather_list(const int *piv, int n, std::vector<int> &idx) {
     }
 }
 
+// Two communicators per GPU.  `comm` (default configuration) carries the one grouped send/recv of the column permutation.
+// `bcast` carries the per-block broadcasts and is limited to MATINV_MULTI_BCAST_CTAS (default 2) CTAs: a receiver's
+// broadcast kernel is launched a whole block step ahead and spins until the owner has factored the panel, so every CTA it
+// holds is an SM slot the trailing GEMM does not get for ~2.5 ms.  Measured on 8 B200 at N=65536 (MATINV_MULTI_TRACE):
+// main stream busy 1474.6 ms with NCCL's default channel count, 1420.7 ms with 2; the main stream waits 1.3 ms in total for
+// messages either way (the exchange is fully hidden behind the GEMM, so its own speed does not matter).
 struct Comms {
     std::mutex mu;
     int ngpu = 0;
-    std::vector<ncclComm_t> comm;
+    std::vector<ncclComm_t> comm, bcast;
 } g_comms;
+
+int bcast_ctas() {
+    const char *e = getenv("MATINV_MULTI_BCAST_CTAS");
+    const int v = e ? atoi(e) : 2;
+    return v;   // <= 0: NCCL's default
+}
+
+void destroy_comms() {
+    for (ncclComm_t c : g_comms.bcast) if (c) g_nccl.CommDestroy(c);
+    for (ncclComm_t c : g_comms.comm) if (c) g_nccl.CommDestroy(c);
+    g_comms.bcast.clear();
+    g_comms.comm.clear();
+    g_comms.ngpu = 0;
+}
 
 int ensure_comms(int ngpu) {
     if (g_comms.ngpu == ngpu) return 0;
     if (!nccl_load()) return shim_fail(MATINV_E_UNSUPPORTED, "NCCL (libnccl.so.2) is not available: multi-GPU entries need it");
-    if (g_comms.ngpu) {
-        for (ncclComm_t c : g_comms.comm) g_nccl.CommDestroy(c);
-        g_comms.comm.clear();
-        g_comms.ngpu = 0;
-    }
+    if (g_comms.ngpu) destroy_comms();
     std::vector<int> devs(ngpu);
     for (int d = 0; d < ngpu; d++) devs[d] = d;
-    g_comms.comm.resize(ngpu);
+    g_comms.comm.assign(ngpu, nullptr);
     int cur = 0;
     cudaGetDevice(&cur);
-    const ncclResult_t r = g_nccl.CommInitAll(g_comms.comm.data(), ngpu, devs.data());
-    cudaSetDevice(cur);
+    ncclResult_t r = g_nccl.CommInitAll(g_comms.comm.data(), ngpu, devs.data());
     if (r != ncclSuccess) {
+        cudaSetDevice(cur);
         g_comms.comm.clear();
         return shim_fail(MATINV_E_CUDA, "ncclCommInitAll(%d) -> %s", ngpu, g_nccl.GetErrorString(r));
     }
+    const int ctas = bcast_ctas();
+    if (ctas > 0) {
+        g_comms.bcast.assign(ngpu, nullptr);
+        ncclUniqueId id;
+        r = g_nccl.GetUniqueId(&id);
+        if (r == ncclSuccess) r = g_nccl.GroupStart();
+        for (int d = 0; d < ngpu && r == ncclSuccess; d++) {
+            ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+            cfg.minCTAs = 1;
+            cfg.maxCTAs = ctas;
+            cudaSetDevice(d);
+            r = g_nccl.CommInitRankConfig(&g_comms.bcast[d], ngpu, id, d, &cfg);
+        }
+        if (r == ncclSuccess) r = g_nccl.GroupEnd();
+        if (r != ncclSuccess) {
+            cudaSetDevice(cur);
+            destroy_comms();
+            return shim_fail(MATINV_E_CUDA, "ncclCommInitRankConfig(maxCTAs = %d) -> %s", ctas, g_nccl.GetErrorString(r));
+        }
+    }
+    cudaSetDevice(cur);
     g_comms.ngpu = ngpu;
     return 0;
 }
@@ -299,7 +340,7 @@ void rank_schedule(int g, Shared &sh, RankState &S) {
         ea.resize(nblk); eb.resize(nblk);
         for (int J = 0; J < nblk; J++) { cudaEventCreate(&ea[J]); cudaEventCreate(&eb[J]); }
     }
-    ncclComm_t comm = (G > 1) ? g_comms.comm[g] : nullptr;
+    ncclComm_t comm = (G > 1) ? (g_comms.bcast.empty() ? g_comms.comm[g] : g_comms.bcast[g]) : nullptr;
     const size_t mbytes = (size_t)matinv_shard_panel_bytes(sh.n);
     RCK(cudaSetDevice(g));
     RCK(cudaEventRecord(S.ev_t0, S.main));
@@ -501,7 +542,9 @@ int run_sharded(const float *A_host, int n, float *X_host, int *piv_host, int ng
     cudaSetDevice(cur);
     if (rc < 0) {
         if (ngpu > 1) {   // a failed rank may have left collectives half-issued: the communicators are not reusable
-            for (ncclComm_t c : g_comms.comm) g_nccl.CommAbort(c);
+            for (ncclComm_t c : g_comms.bcast) if (c) g_nccl.CommAbort(c);
+            for (ncclComm_t c : g_comms.comm) if (c) g_nccl.CommAbort(c);
+            g_comms.bcast.clear();
             g_comms.comm.clear();
             g_comms.ngpu = 0;
         }
@@ -518,9 +561,8 @@ int run_sharded(const float *A_host, int n, float *X_host, int *piv_host, int ng
 
 void multi_shutdown() {
     std::lock_guard<std::mutex> lk(g_comms.mu);
-    if (g_comms.ngpu && g_nccl.h) {
-        for (ncclComm_t c : g_comms.comm) g_nccl.CommDestroy(c);
-    }
+    if (g_comms.ngpu && g_nccl.h) destroy_comms();
+    g_comms.bcast.clear();
     g_comms.comm.clear();
     g_comms.ngpu = 0;
 }

@@ -112,9 +112,13 @@ class CudaShardBackend:
 class ShardedInverter:
     """Host-side schedule of the column-sharded inversion (one instance per rank)."""
 
-    def __init__(self, backend, dist=None):
+    def __init__(self, backend, dist=None, bcast_group=None):
         self.b = backend
         self.dist = dist  # torch.distributed or None when world == 1
+        # process group of the per-block broadcasts (None = default group).  bench.py passes an NCCL group limited to two
+        # CTAs: a receiver's broadcast kernel spins for a whole block step, and every CTA it holds is an SM slot the trailing
+        # GEMM does not get (csrc/gj_multi.cu has the measurement)
+        self.bcast_group = bcast_group
         self.n, self.rank, self.world = backend.n, backend.rank, backend.world
         self.nblk = (self.n + BLOCK - 1) // BLOCK
         self.msg = [backend.new_msg(), backend.new_msg()]
@@ -134,7 +138,7 @@ class ShardedInverter:
             if own == self.rank:
                 self.b.factor(J, msg)
             if self.dist is not None and self.world > 1:
-                self.dist.broadcast(msg, src=own)
+                self.dist.broadcast(msg, src=own, group=self.bcast_group)
             self.b.apply(J, msg)
         return self.b.status()
 
@@ -156,7 +160,7 @@ class ShardedInverter:
         if owner_of(0, self.world) == self.rank:
             self.b.factor(0, msg0)
         if multi:
-            self.dist.broadcast(msg0, src=owner_of(0, self.world))
+            self.dist.broadcast(msg0, src=owner_of(0, self.world), group=self.bcast_group)
         for J in range(self.nblk):
             msg = self.msg[J & 1]
             nxt = J + 1
@@ -176,13 +180,13 @@ class ShardedInverter:
                     side.wait_event(ready)
                     self.b.factor(nxt, nmsg)
                     if multi:
-                        work = self.dist.broadcast(nmsg, src=own_n, async_op=True)
+                        work = self.dist.broadcast(nmsg, src=own_n, async_op=True, group=self.bcast_group)
                 self.b.apply_except(J, msg, nxt)
             else:
                 if multi:
                     with torch.cuda.stream(side):
                         side.wait_event(top)
-                        work = self.dist.broadcast(nmsg, src=own_n, async_op=True)
+                        work = self.dist.broadcast(nmsg, src=own_n, async_op=True, group=self.bcast_group)
                 self.b.apply(J, msg)
             if work is not None:
                 work.wait()                       # main stream waits for the broadcast (no host block)
