@@ -237,14 +237,14 @@ _BCAST_GROUP = None   # (group,) once created
 
 
 def make_bcast_group(dist, world):
-    """NCCL process group for the per-block panel broadcasts, limited to MATINV_SHARD_BCAST_CTAS (default 2) CTAs and on a
+    """NCCL process group for the per-block panel broadcasts, limited to MATINV_SHARD_BCAST_CTAS (default 4) CTAs and on a
     high-priority stream.  A receiver posts the broadcast of panel J+1 a whole block step ahead and its kernel spins until
     the owner has factored the panel: every CTA it holds is an SM slot the trailing GEMM does not get (measured with the
-    C-ABI driver on 8 GPUs, N=65536: 1474.6 ms of main-stream work with NCCL's default channel count, 1420.7 ms with 2;
-    the exchange is hidden behind the GEMM either way, so its own speed does not matter)."""
+    C-ABI driver on 8 GPUs, N=65536: 1493 ms with NCCL's default configuration, 1375 ms with 2 CTAs, 1314 ms with 4, 1738 ms
+    with 1 -- then the broadcast is too slow to hide behind the GEMM)."""
     if world <= 1:
         return None
-    ctas = int(os.environ.get("MATINV_SHARD_BCAST_CTAS", "2"))
+    ctas = int(os.environ.get("MATINV_SHARD_BCAST_CTAS", "4"))
     if ctas <= 0:
         return None
     try:
@@ -304,7 +304,7 @@ def run_sharded_workload(m, torch, dist, n, kind, seed, K, W, rank, world, local
     res = {"n": n, "ms_per_step": ms, "value": 2.0 * n ** 3 / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "steps": K, "warmup": W,
            "n_gpus": world, "scaling": "strong",
            "comm": {"collective": "ncclBroadcast (torch.distributed, high-priority stream"
-                                  + (", process group limited to %s CTAs" % os.environ.get("MATINV_SHARD_BCAST_CTAS", "2") if bgroup is not None else "")
+                                  + (", process group limited to %s CTAs" % os.environ.get("MATINV_SHARD_BCAST_CTAS", "4") if bgroup is not None else "")
                                   + ") of the factored panel per 128-column block + one all_to_all for the deferred column permutation",
                     "bytes_per_block_step": backend.msg_bytes, "block_steps": (n + BLOCK - 1) // BLOCK,
                     "all_to_all_bytes_per_rank": 4 * n * len(backend.blocks) * BLOCK}}

@@ -145,11 +145,12 @@ void column_gather_list(const int *piv, int n, std::vector<int> &idx) {
 }
 
 // Two communicators per GPU.  `comm` (default configuration) carries the one grouped send/recv of the column permutation.
-// `bcast` carries the per-block broadcasts and is limited to MATINV_MULTI_BCAST_CTAS (default 2) CTAs: a receiver's
+// `bcast` carries the per-block broadcasts and is limited to MATINV_MULTI_BCAST_CTAS (default 4) CTAs: a receiver's
 // broadcast kernel is launched a whole block step ahead and spins until the owner has factored the panel, so every CTA it
-// holds is an SM slot the trailing GEMM does not get for ~2.5 ms.  Measured on 8 B200 at N=65536 (MATINV_MULTI_TRACE):
-// main stream busy 1474.6 ms with NCCL's default channel count, 1420.7 ms with 2; the main stream waits 1.3 ms in total for
-// messages either way (the exchange is fully hidden behind the GEMM, so its own speed does not matter).
+// holds is an SM slot the trailing GEMM does not get for ~2.5 ms.  Measured on 8 B200 at N=65536 (factorisation + column
+// exchange; MATINV_MULTI_TRACE splits busy / stalled time of the main stream): NCCL's default configuration 1493 ms (main
+// stream busy 1474.6 ms, stalled 1.3 ms); maxCTAs = 1: 1738 ms (busy 1287 ms -- the interference is gone -- but stalled
+// 425 ms, the broadcast is now too slow to hide); 2: 1375 ms; 4: 1314 ms = 7.88 x the 10.36 s of one GPU.
 struct Comms {
     std::mutex mu;
     int ngpu = 0;
@@ -158,7 +159,7 @@ struct Comms {
 
 int bcast_ctas() {
     const char *e = getenv("MATINV_MULTI_BCAST_CTAS");
-    const int v = e ? atoi(e) : 2;
+    const int v = e ? atoi(e) : 4;
     return v;   // <= 0: NCCL's default
 }
 

@@ -590,10 +590,20 @@ cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long l
                             int sw, float *CmT, long long ldc, int *piv, float *pv, int *info, cudaStream_t st) {
 #define SP_ARGS in, ld_in, out, ld_out, n, k0, s0, sw, CmT, ldc, piv, pv, info, st
     if (const int f = forced_shape(); f && n <= forced_capacity(f)) {
-        if (f == 1) return launch_subpanel_t<16, 2, 512>(16, SP_ARGS);
-        if (f == 2) return launch_subpanel_t<16, 4, 256>(16, SP_ARGS);
-        if (f == 3) return launch_subpanel_t<16, 4, 512>(16, SP_ARGS);
-        return launch_subpanel_t<8, 8, 512>(16, SP_ARGS);
+        // smallest power-of-two cluster that holds n rows (MATINV_SUBPANEL_CTAS overrides, e.g. 16 = the production size)
+        static int forced_ctas = -1;
+        if (forced_ctas < 0) {
+            const char *e = getenv("MATINV_SUBPANEL_CTAS");
+            forced_ctas = e ? atoi(e) : 0;
+        }
+        const int rows_per_cta = (f == 1) ? 1024 : (f == 2) ? 1024 : (f == 3) ? 2048 : 4096;
+        int ncta = 1;
+        while (ncta * rows_per_cta < n) ncta *= 2;
+        if (forced_ctas > 0 && forced_ctas >= ncta && forced_ctas <= 16) ncta = forced_ctas;
+        if (f == 1) return launch_subpanel_t<16, 2, 512>(ncta, SP_ARGS);
+        if (f == 2) return launch_subpanel_t<16, 4, 256>(ncta, SP_ARGS);
+        if (f == 3) return launch_subpanel_t<16, 4, 512>(ncta, SP_ARGS);
+        return launch_subpanel_t<8, 8, 512>(ncta, SP_ARGS);
     }
     if (n <= 8192) {
         int ncta = 1;

@@ -365,9 +365,14 @@ def test_subpanel_shapes_bit_identical(m, shape):
     env = {k: v for k, v in os.environ.items() if not k.startswith("MATINV_")}
     env["MATINV_SUBPANEL_SHAPE"] = shape
     env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
-    r = subprocess.run([sys.executable, "-c", _SHAPE_PROBE, "300", "1100", "2100"], env=env, cwd=root, capture_output=True,
-                       text=True, timeout=900)
-    assert r.returncode == 0 and "SHAPE-OK" in r.stdout, r.stderr[-3000:]
+    for ctas in ("16", None):      # the production cluster size (16 CTAs, most of them without rows here) and the smallest that fits
+        if ctas:
+            env["MATINV_SUBPANEL_CTAS"] = ctas
+        else:
+            env.pop("MATINV_SUBPANEL_CTAS", None)
+        r = subprocess.run([sys.executable, "-c", _SHAPE_PROBE, "300", "1100", "2100"], env=env, cwd=root, capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0 and "SHAPE-OK" in r.stdout, (ctas, r.stderr[-3000:])
 
 
 @pytest.mark.parametrize("n", [8320, 16384])

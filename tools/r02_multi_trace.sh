@@ -13,9 +13,10 @@ for i in range(3):
     rc, piv, ms = m.sharded_synthetic(n, SEED_UNIFORM + n, "uniform", ngpu=8)
     print("run", i, "rc", rc, "compute_ms (factor + exchange)", ms, flush=True)
 PY
-  echo "== $name"; grep -E "compute_ms|trace\] rank 0" $O/r02_trace_$name.txt | tail -6
+  echo "== $name"; grep -E "compute_ms|trace\] rank 0" $O/r02_trace_$name.txt | tail -4
 }
-run ctas1 MATINV_MULTI_BCAST_CTAS=1 MATINV_MULTI_TRACE=1
-run ctas2 MATINV_MULTI_BCAST_CTAS=2
-run ctas4 MATINV_MULTI_BCAST_CTAS=4
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --workload n65536 --steps 2 --warmup 1 > $O/r02_bench_sh65536_g8.json 2> $O/r02_bench_sh65536_g8.err; tail -c 1800 $O/r02_bench_sh65536_g8.json; tail -2 $O/r02_bench_sh65536_g8.err
+run ctas3 MATINV_MULTI_BCAST_CTAS=3
+run ctas6 MATINV_MULTI_BCAST_CTAS=6
+run ctas8 MATINV_MULTI_BCAST_CTAS=8 MATINV_MULTI_TRACE=1
+run ctas4 MATINV_MULTI_BCAST_CTAS=4 MATINV_MULTI_TRACE=1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 5 --warmup 3 > $O/r02_bench_default_g8.json 2> $O/r02_bench_default_g8.err; tail -c 1500 $O/r02_bench_default_g8.json; tail -2 $O/r02_bench_default_g8.err
