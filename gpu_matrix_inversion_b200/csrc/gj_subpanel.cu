@@ -570,12 +570,14 @@ static int forced_shape() {
                 else if (w == 16 && r == 4 && th == 256) shape = 2;
                 else if (w == 16 && r == 4 && th == 512) shape = 3;
                 else if (w == 8 && r == 8 && th == 512) shape = 4;
+                else if (w == 16 && r == 1 && th == 256) shape = 5;
+                else if (w == 16 && r == 1 && th == 512) shape = 6;
             }
         }
     }
     return shape;
 }
-static int forced_capacity(int shape) { return shape == 1 ? 16384 : shape == 2 ? 16384 : shape == 3 ? 32768 : shape == 4 ? 65536 : 0; }
+static int forced_capacity(int shape) { return shape == 1 ? 16384 : shape == 2 ? 16384 : shape == 3 ? 32768 : shape == 4 ? 65536 : shape == 5 ? 4096 : shape == 6 ? 8192 : 0; }
 
 int subpanel_width(int n) {
     const int f = forced_shape();
@@ -596,14 +598,24 @@ cudaError_t launch_subpanel(const float *in, long long ld_in, float *out, long l
             const char *e = getenv("MATINV_SUBPANEL_CTAS");
             forced_ctas = e ? atoi(e) : 0;
         }
-        const int rows_per_cta = (f == 1) ? 1024 : (f == 2) ? 1024 : (f == 3) ? 2048 : 4096;
+        const int rows_per_cta = (f == 1) ? 1024 : (f == 2) ? 1024 : (f == 3) ? 2048 : (f == 5) ? 256 : (f == 6) ? 512 : 4096;
         int ncta = 1;
         while (ncta * rows_per_cta < n) ncta *= 2;
         if (forced_ctas > 0 && forced_ctas >= ncta && forced_ctas <= 16) ncta = forced_ctas;
         if (f == 1) return launch_subpanel_t<16, 2, 512>(ncta, SP_ARGS);
         if (f == 2) return launch_subpanel_t<16, 4, 256>(ncta, SP_ARGS);
         if (f == 3) return launch_subpanel_t<16, 4, 512>(ncta, SP_ARGS);
+        if (f == 5) return launch_subpanel_t<16, 1, 256>(ncta, SP_ARGS);
+        if (f == 6) return launch_subpanel_t<16, 1, 512>(ncta, SP_ARGS);
         return launch_subpanel_t<8, 8, 512>(ncta, SP_ARGS);
+    }
+    if (n <= 4096) {
+        // more, smaller CTAs: the per-step chain (warp redux -> CTA arg max -> mailbox exchange) shortens with the CTA, and at
+        // these orders the panel chain is the critical path (N=4096: 12.10 -> 11.67 ms, N=2048: 5.43 -> 5.18 ms;
+        // profiles/r02_subpanel_shapes_small_n.txt)
+        int ncta = 1;
+        while (ncta * 256 < n) ncta *= 2;
+        return launch_subpanel_t<16, 1, 256>(ncta, SP_ARGS);
     }
     if (n <= 8192) {
         int ncta = 1;

@@ -351,7 +351,7 @@ print("SHAPE-OK")
 """
 
 
-@pytest.mark.parametrize("shape", ["16x2x512", "16x4x256", "16x4x512", "8x8x512"])
+@pytest.mark.parametrize("shape", ["16x1x512", "16x2x512", "16x4x256", "16x4x512", "8x8x512"])
 def test_subpanel_shapes_bit_identical(m, shape):
     """The sub-panel kernel instantiations that only the large orders select -- <16,4,256> (N >= 15360), <16,4,512>
     (16384 < N <= 32768) and <8,8,512> with 8-wide sub-panels (N > 32768, i.e. BASELINE config 5) -- forced through
