@@ -98,6 +98,10 @@ int matinv_nccl_version(void);
  * The host (Python + torch.distributed, or any MPI-like launcher) owns the exchange step; these
  * calls own the math.  Columns are dealt block-cyclically in blocks of 128: global column block J
  * lives on rank J % world.  See DESIGN.md "multi-GPU". */
+/* Thread-safety: handles are independent; one host thread per device may drive its own handle concurrently (that is what the
+ * single-call entries above do).  Do not run MATINV_FLAG_TF32X3 inversions concurrently with them: that mode switches the
+ * panel kernels to their critical-path shapes process-wide (results are unaffected -- the shapes are bit-identical -- but the
+ * tuning is not). */
 typedef struct matinv_shard matinv_shard_t;
 /* panel message: what the owner of block J broadcasts.  Size in bytes for a given n. */
 long long matinv_shard_panel_bytes(int n);
