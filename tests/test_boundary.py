@@ -48,6 +48,29 @@ def test_python_twin_argument_conventions_without_device():
             m.invert_batched(np.zeros((1, 4, 4), np.float32))
 
 
+def test_multi_gpu_entries_argument_checks_without_device():
+    """The single-call multi-GPU entries (csrc/gj_multi.cu) validate their arguments before touching a device and, like every
+    compute entry, fail loudly without one (no CPU fallback)."""
+    import gpu_matrix_inversion_b200 as m
+
+    A = np.eye(4, dtype=np.float32)
+    X = np.empty_like(A)
+    assert m.lib.matinv_invert_sharded_f32(A.ctypes.data, 0, X.ctypes.data, None, 1, 0, 0) == m.E_INVALID
+    assert m.lib.matinv_invert_sharded_f32(None, 4, X.ctypes.data, None, 1, 0, 0) == m.E_INVALID
+    assert m.lib.matinv_invert_sharded_f32(A.ctypes.data, 4, X.ctypes.data, None, 1, 64, 0) == m.E_UNSUPPORTED      # nb must be 0 / 128
+    assert m.lib.matinv_invert_sharded_f32(A.ctypes.data, 4, X.ctypes.data, None, 1, 0, m.FLAG_TF32X3) == m.E_UNSUPPORTED
+    B = np.zeros((2, 4, 4), np.float32)
+    assert m.lib.matinv_invert_batched_f32_ngpu(B.ctypes.data, 200, 2, B.ctypes.data, None, 1, 0) == m.E_INVALID       # n > 128
+    assert m.lib.matinv_invert_batched_f32_ngpu(B.ctypes.data, 4, 0, B.ctypes.data, None, 1, 0) == m.OK               # empty batch
+    if m.device_count() == 0:
+        assert m.lib.matinv_invert_sharded_f32(A.ctypes.data, 4, X.ctypes.data, None, 1, 0, 0) == m.E_NODEVICE
+        assert m.lib.matinv_invert_batched_f32_ngpu(B.ctypes.data, 4, 2, B.ctypes.data, None, 1, 0) == m.E_NODEVICE
+        assert m.lib.matinv_sharded_synthetic_f32(256, 1, 0, 1, None, None) == m.E_NODEVICE
+        with pytest.raises(m.MatinvError):
+            m.invert_sharded(A, ngpu=1)
+        assert m.last_phases() is None
+
+
 def test_cpp_surface_links_and_follows_conventions(tmp_path):
     """Compile a caller against include/mat_inv_32.h exactly like a user of the reference header."""
     src = tmp_path / "caller.cpp"
