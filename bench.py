@@ -434,10 +434,18 @@ def main():
         torch.cuda.synchronize()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / K)
         assert rc == m.OK
+        # the host entry uploads A in column windows while it already factors (pipelined schedule): same bits as the device entry
+        Xchk = torch.empty_like(X)
+        Xchk.copy_(Xh)
+        e2e_same = bool(torch.equal(Xchk.view(torch.int32), X.view(torch.int32)))
+        del Xchk
+        assert e2e_same, "host-entry result differs from the device-entry result"
         e2e = {"value": world * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n,
+               "bitwise_equal_device_result": e2e_same,
                "d2h_bytes_per_step": 4 * n * n, "ms_per_step": e2e_s * 1e3,
                "phases_s": m.last_phases(),   # last step: setup / H2D / factorisation / extraction + D2H / total (matinv_last_phases)
-               "api": "matinv_invert_f32 (what matrix_inv_32 calls), pinned host buffers"}
+               "api": "matinv_invert_f32 (what matrix_inv_32 calls), pinned host buffers; upload pipelined in column windows "
+                      "(MATINV_H2D_PIPELINE, default on for n >= 8192)"}
 
         # optional 3xTF32 tcgen05 trailing update (north_star config 3: "FP32 SIMT vs 3xTF32 tcgen05"), same input, same K;
         # the residual gate (O(N^2) probe + status read-back) is inside the timed region.  Its dominant kernel is HBM-bound.

@@ -75,6 +75,21 @@ __global__ void __launch_bounds__(512) extract_kernel(const float *__restrict__ 
     if (check && __syncthreads_or(bad) && threadIdx.x == 0) atomicCAS(info, 0, -1);
 }
 
+// columns [c0, c0 + ncols) only (c0 + ncols <= npad): the host entry uploads A in column windows and loads each on arrival
+__global__ void __launch_bounds__(256) load_window_kernel(const float *__restrict__ A, int n, float *__restrict__ W,
+                                                          long long ld, int c0, int ncols) {
+    const long long i = blockIdx.x;
+    const int jj = blockIdx.y * 256 + threadIdx.x;
+    if (jj >= ncols) return;
+    const int j = c0 + jj;
+    W[i * ld + j] = (i < n && j < n) ? A[i * (long long)n + j] : 0.0f;
+}
+
+void launch_load_window(const float *A, int n, float *W, long long ld, int npad, int c0, int ncols, cudaStream_t st) {
+    dim3 grid(npad, (ncols + 255) / 256);
+    load_window_kernel<<<grid, 256, 0, st>>>(A, n, W, ld, c0, ncols);
+}
+
 void launch_load(const float *A, int n, float *W, long long ld, int npad, cudaStream_t st) {
     dim3 grid(npad, (npad + 255) / 256);
     load_kernel<<<grid, 256, 0, st>>>(A, n, W, ld, npad);

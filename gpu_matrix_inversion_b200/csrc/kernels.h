@@ -81,6 +81,7 @@ void launch_extract(const float *W, long long ld, int n, const int *colsrc, floa
 void launch_extract_rows(const float *W, long long ld, int n, const int *colsrc, float *X, int *info, int check, int row0,
                          int nrows, cudaStream_t st);
 void launch_load(const float *A, int n, float *W, long long ld, int npad, cudaStream_t st);
+void launch_load_window(const float *A, int n, float *W, long long ld, int npad, int c0, int ncols, cudaStream_t st);
 
 // ---- gj_batched.cu : n <= 128, one CTA per matrix
 cudaError_t launch_batched(const float *A, int n, long long batch, float *X, int *info, cudaStream_t st);

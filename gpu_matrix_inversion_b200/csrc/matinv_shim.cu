@@ -104,6 +104,11 @@ struct Workspace {
     float *tcA[2] = {nullptr, nullptr}, *tcB[2] = {nullptr, nullptr};
     double *probe = nullptr;
     int tc_npad = 0;
+    // pipelined upload (host entry): the multipliers / pivot values / row permutation of the first panels are kept until the
+    // last column window has caught up
+    std::vector<float *> ringC, ringPv;
+    std::vector<PanelState *> ringPs;
+    int ring_npad = 0;
 };
 
 // Everything cached between calls belongs to exactly one device; one cache per device so that callers (or threads)
@@ -120,6 +125,7 @@ struct DeviceCache {
     size_t hostio_i_bytes = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t ev_h0 = nullptr, ev_f = nullptr;   // phase boundaries: before H2D, after the factorisation
+    cudaEvent_t ev_up[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // column windows uploaded
     cudaStream_t copy_stream = nullptr;   // D2H of finished row chunks, overlapped with the extraction of the next chunk
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     cudaStream_t panel_stream = nullptr;  // high priority: the latency-critical panel kernels
@@ -163,6 +169,9 @@ void free_ws(Workspace &w) {
     cudaFree(w.piv); cudaFree(w.colsrc); cudaFree(w.info); cudaFree(w.ps);
     cudaFree(w.CmT2); cudaFree(w.pv2); cudaFree(w.ps2);
     cudaFree(w.tcA[0]); cudaFree(w.tcA[1]); cudaFree(w.tcB[0]); cudaFree(w.tcB[1]); cudaFree(w.probe);
+    for (float *p : w.ringC) cudaFree(p);
+    for (float *p : w.ringPv) cudaFree(p);
+    for (PanelState *p : w.ringPs) cudaFree(p);
     w = Workspace();
 }
 
@@ -185,6 +194,7 @@ void release_locked() {
     if (G.stream) {
         cudaEventDestroy(G.ev[0]); cudaEventDestroy(G.ev[1]);
         cudaEventDestroy(G.ev_h0); cudaEventDestroy(G.ev_f);
+        for (int i = 0; i < 8; i++) cudaEventDestroy(G.ev_up[i]);
         cudaStreamDestroy(G.stream);
         G.stream = nullptr;
     }
@@ -241,6 +251,7 @@ int ensure_stream() {
         CK(cudaEventCreate(&G.ev[1]));
         CK(cudaEventCreate(&G.ev_h0));
         CK(cudaEventCreate(&G.ev_f));
+        for (int i = 0; i < 8; i++) CK(cudaEventCreateWithFlags(&G.ev_up[i], cudaEventDisableTiming));
     }
     return 0;
 }
@@ -472,16 +483,218 @@ void schedule_lookahead(Workspace &w, int n, cudaStream_t st) {
     }
 }
 
+// ---- pipelined upload (host entry only) -----------------------------------------------------------------------------
+// The matrix arrives over PCIe in NW column windows (window 0 first).  The factorisation starts as soon as window 0 is on
+// the device; window w joins at panel act[w]: the stream waits for its upload, loads it into W and applies the panels it
+// missed (0 .. act[w]-1, whose multipliers / pivot values / row permutations are kept in a ring) before taking part in panel
+// act[w].  Every element still receives the panels' updates in order, so the result is bit-identical; only the 1/NW of the
+// upload that precedes the first panel stays exposed.  Requirement: act[w] <= first block of window w - 1 (the look-ahead
+// block k+1 of every panel must already be active), checked by plan_pipeline.
+struct PipePlan {
+    int nwin = 0;
+    int c0[8], ncols[8], act[8];
+    int ringfix = 0;   // panels 0 .. ringfix-1 keep their own ring slot, later panels alternate between two more
+};
+
+bool h2d_pipeline_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("MATINV_H2D_PIPELINE");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+bool use_lookahead(int n, int npad);
+
+// Column windows and activation panels for order n; false = do not pipeline this order.
+bool plan_pipeline(int n, int npad, int flags, PipePlan &P) {
+    if (!h2d_pipeline_enabled() || n < 8192 || (flags & (MATINV_FLAG_TF32X3 | MATINV_FLAG_UNBLOCKED))) return false;
+    if (!use_lookahead(n, npad) || lookahead_mode() < 2) return false;
+    static int nwin_env = -1;
+    if (nwin_env < 0) {
+        const char *e = getenv("MATINV_H2D_WINDOWS");
+        nwin_env = e ? atoi(e) : 0;
+    }
+    const int nt = npad / MATINV_NB;
+    int nw = nwin_env;
+    if (nw == 0) {   // default: as many windows as leave the first one at least 8 blocks wide, at most 5
+        nw = 5;      // (N=16384, pinned buffers: e2e 205.3 ms unpipelined, 203.3 / 200.4 / 199.0 / 198.0 ms with 2 / 3 / 4 / 5)
+        while (nw > 2 && (nt >> (nw - 1)) < 8) nw--;
+    }
+    if (nw < 2 || nw > 6 || nt < 64) return false;
+    // Geometric windows: the first one (the only upload that stays exposed) is small, each later one twice as wide --
+    // cumulative boundaries 1/2^(nw-1), ..., 1/4, 1/2, 1 of the tile count.  Few joins, and the windows that join late are the
+    // wide ones whose catch-up is efficient GEMM work.
+    int bound[8];
+    for (int w = 0; w < nw; w++) bound[w] = (w == nw - 1) ? nt : (nt >> (nw - 1 - w));
+    if (bound[0] < 8) return false;
+    // When does window w land, and which panel is the factorisation at by then?  Model: PCIe at 50 GB/s; a panel step takes
+    // max(panel chain, trailing update of the active columns) with the chain ~0.5 ms and the update ~1.31 ms at n = 16384
+    // and every column active; a joining window replays the panels it missed.  A window joins at the first panel whose start
+    // lies 10 % after its upload is due (joining early would stall the stream on the copy; joining late only lengthens the
+    // replay), and no later than the panel before its first block becomes the look-ahead block.
+    const double scale = (double)n / 16384.0;
+    const double t_chain = 0.5e-3 * scale, t_full = 1.31e-3 * scale * scale, t_row = 35e-6;
+    const double bw = 50e9;
+    P.nwin = nw;
+    P.ringfix = 0;
+    double due[8];
+    for (int w = 0; w < nw; w++) {
+        P.c0[w] = (w == 0 ? 0 : bound[w - 1]) * MATINV_NB;
+        P.ncols[w] = (bound[w] - (w == 0 ? 0 : bound[w - 1])) * MATINV_NB;
+        due[w] = (double)n * (double)bound[w] * MATINV_NB * 4.0 / bw;
+        P.act[w] = 0;
+    }
+    double t = due[0];
+    int active = 1;
+    const int nblk = (n + MATINV_NB - 1) / MATINV_NB;
+    for (int k = 0; k < nblk && active < nw; k++) {
+        while (active < nw) {
+            const int latest = P.c0[active] / MATINV_NB - 1;
+            if (k < latest && t < 1.1 * due[active]) break;
+            if (k < 1) break;
+            P.act[active] = k;
+            t += k * (t_full * (double)P.ncols[active] / (double)npad + t_row);   // replay of the panels it missed
+            active++;
+        }
+        const double f = (double)(P.c0[active - 1] + P.ncols[active - 1]) / (double)npad;
+        const double work = t_full * f + t_row;
+        t += (work > t_chain) ? work : t_chain;
+    }
+    for (int w = 1; w < nw; w++) {
+        if (P.act[w] < 1) P.act[w] = P.c0[w] / MATINV_NB - 1;   // (not reached by the model: join at the last possible panel)
+        if (P.act[w] < P.act[w - 1]) P.act[w] = P.act[w - 1];
+        if (P.act[w] > P.ringfix) P.ringfix = P.act[w];
+    }
+    return true;
+}
+
+int ensure_ring(Workspace &w, int slots) {
+    if (w.ring_npad != w.npad) {
+        for (float *p : w.ringC) cudaFree(p);
+        for (float *p : w.ringPv) cudaFree(p);
+        for (PanelState *p : w.ringPs) cudaFree(p);
+        w.ringC.clear(); w.ringPv.clear(); w.ringPs.clear();
+        w.ring_npad = w.npad;
+    }
+    bool grew = false;
+    while ((int)w.ringC.size() < slots) {
+        float *c = nullptr, *pv = nullptr;
+        PanelState *ps = nullptr;
+        CK(cudaMalloc(&c, (size_t)MATINV_NB * w.npad * sizeof(float)));
+        w.ringC.push_back(c);
+        CK(cudaMemset(c, 0, (size_t)MATINV_NB * w.npad * sizeof(float)));
+        CK(cudaMalloc(&pv, MATINV_NB * sizeof(float)));
+        w.ringPv.push_back(pv);
+        CK(cudaMalloc(&ps, sizeof(PanelState)));
+        w.ringPs.push_back(ps);
+        grew = true;
+    }
+    if (grew) CK(cudaDeviceSynchronize());   // null-stream memsets vs non-blocking streams (see ensure_ws)
+    return 0;
+}
+
+// trailing update of panel k on the columns [c0, c0 + ncols); the tiles of blocks k and k+1 that fall into the range are
+// left out (block k is the panel itself, block k+1 is updated on the panel stream)
+void range_update(Workspace &w, int c0, int ncols, int k, int kb, bool skip_next, const float *CmT, const float *pv,
+                  const PanelState *ps, cudaStream_t st) {
+    const long long ld = w.npad;
+    const int nt = w.npad / MATINV_NB;
+    const int t0 = c0 / MATINV_NB, wt = ncols / MATINV_NB;
+    int s_lo = k, s_hi = skip_next ? k + 2 : k + 1;   // global tiles [s_lo, s_hi) to leave out
+    if (s_lo < t0) s_lo = t0;
+    if (s_hi > t0 + wt) s_hi = t0 + wt;
+    const int skip_n = (s_hi > s_lo) ? s_hi - s_lo : 0;
+    const int skip = skip_n ? s_lo - t0 : -1;
+    if (skip_n == wt) return;
+    launch_rowblock_ex(w.W + c0, ld, ncols, k * MATINV_NB, kb, skip_n ? skip : 0, skip_n, CmT, ld, pv, ps, w.U + c0, ld, st);
+    launch_trailing_gemm_ex(w.W + c0, ld, nt, wt, k, skip, skip_n, kb, CmT, ld, w.U + c0, ld, st);
+    COUNT_LAUNCH(2);
+}
+
+// schedule_lookahead (mode 2) with column windows joining as their upload completes; A_dev is the n x n staging buffer the
+// windows are copied into (ev_up[w] recorded on the copy stream after window w)
+void schedule_lookahead_pipelined(Workspace &w, const float *A_dev, int n, cudaStream_t st, const PipePlan &P) {
+    const long long ld = w.npad;
+    const int nt = w.npad / MATINV_NB;
+    const int nblk = (n + MATINV_NB - 1) / MATINV_NB;
+    cudaStream_t sp = G.panel_stream;
+    auto slot = [&](int k) { return k < P.ringfix ? k : P.ringfix + (k & 1); };
+    static int critical_env = -1;
+    if (critical_env < 0) {
+        const char *e = getenv("MATINV_H2D_CRITICAL");
+        critical_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool critical_phase = critical_env == 1;
+    if (critical_phase) panel_set_critical(1);
+    cudaStreamWaitEvent(st, G.ev_up[0], 0);
+    launch_load_window(A_dev, n, w.W, ld, w.npad, P.c0[0], P.ncols[0], st);
+    COUNT_LAUNCH(1 + launch_panel_factor(w.W, ld, n, 0, (n < MATINV_NB) ? n : MATINV_NB, w.ringC[slot(0)], ld, w.piv, w.ringPv[slot(0)],
+                                         w.info, w.ringPs[slot(0)], w.P[0], w.P[1], st));
+    int nactive = 1;
+    for (int k = 0; k < nblk; k++) {
+        const int k0 = k * MATINV_NB;
+        const int kb = (n - k0 < MATINV_NB) ? n - k0 : MATINV_NB;
+        while (nactive < P.nwin && P.act[nactive] <= k) {   // a window joins: upload done -> load -> the panels it missed
+            const int wi = nactive++;
+            cudaStreamWaitEvent(st, G.ev_up[wi], 0);
+            launch_load_window(A_dev, n, w.W, ld, w.npad, P.c0[wi], P.ncols[wi], st);
+            COUNT_LAUNCH(1);
+            for (int j = 0; j < k; j++)
+                range_update(w, P.c0[wi], P.ncols[wi], j, MATINV_NB, true, w.ringC[slot(j)], w.ringPv[slot(j)], w.ringPs[slot(j)], st);
+        }
+        // the windows that have joined form one contiguous prefix: ONE pivot-row kernel and ONE update per panel (the pivot-row
+        // kernel is a latency chain -- one launch per window costs 35 us each, measured +20 ms per inversion with 4 windows)
+        const int cend = P.c0[nactive - 1] + P.ncols[nactive - 1];
+        const int s = slot(k);
+        if (k + 1 < nblk) {
+            const int k1 = k0 + MATINV_NB;
+            const int kb1 = (n - k1 < MATINV_NB) ? n - k1 : MATINV_NB;
+            const int s1 = slot(k + 1);
+            cudaEventRecord(G.ev_a, st);
+            cudaStreamWaitEvent(sp, G.ev_a, 0);
+            // while windows are still missing the update is short and the panel chain is the critical path: use the panel
+            // kernels' fast shapes (as the tensor-core mode does), the hidden-behind-the-GEMM shapes afterwards
+            if (critical_phase) panel_set_critical(nactive < P.nwin ? 1 : 0);
+            launch_rowblock_ex(w.W + k1, ld, MATINV_NB, k0, kb, 0, 0, w.ringC[s], ld, w.ringPv[s], w.ringPs[s], w.U + k1, ld, sp);
+            launch_trailing_gemm_ex(w.W + k1, ld, nt, 1, k, -1, 0, kb, w.ringC[s], ld, w.U + k1, ld, sp);
+            COUNT_LAUNCH(2 + launch_panel_factor(w.W + k1, ld, n, k1, kb1, w.ringC[s1], ld, w.piv, w.ringPv[s1], w.info, w.ringPs[s1], w.P[0],
+                                                 w.P[1], sp));
+            cudaEventRecord(G.ev_p, sp);
+            range_update(w, 0, cend, k, kb, true, w.ringC[s], w.ringPv[s], w.ringPs[s], st);
+            cudaStreamWaitEvent(st, G.ev_p, 0);
+        } else {
+            range_update(w, 0, cend, k, kb, false, w.ringC[s], w.ringPv[s], w.ringPs[s], st);
+        }
+    }
+    panel_set_critical(0);
+}
+
 bool use_lookahead(int n, int npad) {
     return lookahead_mode() >= 1 && use_panel_v1(n) && npad >= 8 * MATINV_NB;
 }
 
 // load + factorisation + column gather list; leaves M = inv(P A) in the workspace
-int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags) {
+int factor_locked(const float *A_dev, int n, cudaStream_t st, int flags, const PipePlan *plan = nullptr) {
     const int npad = ((n + MATINV_NB - 1) / MATINV_NB) * MATINV_NB;
     int rc = ensure_ws(npad);
     if (rc) return rc;
     Workspace &w = G.ws;
+    if (plan) {   // host entry with a pipelined upload: the windows of A_dev arrive while the factorisation runs
+        rc = ensure_ring(w, plan->ringfix + 2);
+        if (rc) return rc;
+        rc = ensure_lookahead();
+        if (rc) return rc;
+        g_tc.on = g_tc.used = false;
+        g_sched_err = cudaSuccess;
+        CK(cudaMemsetAsync(w.info, 0, sizeof(int), st));
+        schedule_lookahead_pipelined(w, A_dev, n, st, *plan);
+        COUNT_LAUNCH(3);
+        launch_colperm_build(w.piv, n, w.colsrc, st);
+        CK(cudaGetLastError());
+        return 0;
+    }
     g_tc.on = g_tc.used = false;
     if ((flags & MATINV_FLAG_TF32X3) && !(flags & MATINV_FLAG_UNBLOCKED) && npad > MATINV_NB) {
         rc = ensure_tc(w);
@@ -649,9 +862,28 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
     if (rc) return rc;
     cudaStream_t st = G.stream;
     const double t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    PipePlan plan;
+    const int npad_h = ((n + MATINV_NB - 1) / MATINV_NB) * MATINV_NB;
+    const bool piped = plan_pipeline(n, npad_h, flags, plan);
     nvtxRangePushA("H2D");
     CK(cudaEventRecord(G.ev_h0, st));
-    CK(cudaMemcpyAsync(G.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
+    if (piped) {
+        // column windows over the copy stream, window 0 first; the factorisation (on st) only waits for window 0 and lets the
+        // others join as they land (schedule_lookahead_pipelined)
+        rc = ensure_copy_stream();
+        if (rc) { nvtxRangePop(); return rc; }
+        for (int wi = 0; wi < plan.nwin; wi++) {
+            const int c0 = plan.c0[wi];
+            const int c1 = (c0 + plan.ncols[wi] < n) ? c0 + plan.ncols[wi] : n;
+            if (c1 > c0)
+                CK(cudaMemcpy2DAsync(G.hostio + c0, (size_t)n * sizeof(float), A_host + c0, (size_t)n * sizeof(float),
+                                     (size_t)(c1 - c0) * sizeof(float), (size_t)n, cudaMemcpyHostToDevice, G.copy_stream));
+            CK(cudaEventRecord(G.ev_up[wi], G.copy_stream));
+        }
+        CK(cudaStreamWaitEvent(st, G.ev_up[0], 0));
+    } else {
+        CK(cudaMemcpyAsync(G.hostio, A_host, bytes, cudaMemcpyHostToDevice, st));
+    }
     CK(cudaEventRecord(G.ev[0], st));
     nvtxRangePop();
     if (flags & MATINV_FLAG_TF32X3) {
@@ -680,9 +912,12 @@ int matinv_invert_f32(const float *A_host, int n, float *X_host, int *piv_host, 
         return rc;
     }
     nvtxRangePushA("factorisation (enqueue)");
-    rc = factor_locked(G.hostio, n, st, flags);
+    rc = factor_locked(G.hostio, n, st, flags, piped ? &plan : nullptr);
     nvtxRangePop();
-    if (rc) return rc;
+    if (rc) {
+        if (piped) cudaStreamSynchronize(G.copy_stream);   // the window uploads read the caller's buffer
+        return rc;
+    }
     CK(cudaEventRecord(G.ev_f, st));
     NvtxRange tail("extraction + D2H");
     // extraction (deferred column permutation + isfinite scan) in row chunks, each chunk's D2H copy overlapped with the

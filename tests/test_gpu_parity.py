@@ -454,3 +454,46 @@ def test_phase_timers(m):
     assert ph["factor"] > 0.0 and ph["total"] >= ph["factor"]
     t = m.last_timing()
     assert t is not None and abs(t[0] - ph["total"]) < 1e-9
+
+
+_PIPE_PROBE = r"""
+import hashlib, sys
+import numpy as np, torch
+import gpu_matrix_inversion_b200 as m
+from oracle.gj_oracle import SEED_UNIFORM
+out = []
+for n in (int(a) for a in sys.argv[1:]):
+    A = m.generate_dev(n, SEED_UNIFORM + n, "uniform").cpu().numpy()
+    X, piv = m.invert(A, want_piv=True)
+    assert X is not None
+    out.append(hashlib.sha256(piv.tobytes() + X.tobytes()).hexdigest())
+    S = A.copy(); S[:, n - 3] = 0.0            # singular in the LAST column window
+    assert m.invert(S) is None
+    ph = m.last_phases()
+print("PIPE", *out)
+"""
+
+
+def test_pipelined_upload_bit_identical(m):
+    """The host entry uploads A in column windows and starts factoring when the first one has landed; later windows join at
+    a later panel and replay the panels they missed (csrc/matinv_shim.cu:schedule_lookahead_pipelined).  Same bits as the
+    plain upload (MATINV_H2D_PIPELINE=0) and, at N=8320, as the oracle's committed hash -- for the default 4 windows, for 3 and 2, and
+    for a ragged order (9001) whose last window carries the padding."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = json.loads((Path(__file__).parent / "golden" / "large_sha256.json").read_text())
+    seen = []
+    for extra in ({"MATINV_H2D_PIPELINE": "0"}, {}, {"MATINV_H2D_WINDOWS": "3"}, {"MATINV_H2D_WINDOWS": "2"}):
+        env = {k: v for k, v in os.environ.items() if not k.startswith("MATINV_")}
+        env.update(extra)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        r = subprocess.run([sys.executable, "-c", _PIPE_PROBE, "8320", "9001"], env=env, cwd=root, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (extra, r.stderr[-3000:])
+        seen.append([l for l in r.stdout.splitlines() if l.startswith("PIPE")][-1].split()[1:])
+    assert all(h == seen[0] for h in seen[1:]), seen
+    assert seen[0][0] == gold["8320"]["sha256_piv_X"]
