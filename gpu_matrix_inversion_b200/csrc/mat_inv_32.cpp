@@ -24,12 +24,10 @@ std::vector<float> matrix_inv_32(std::vector<float> matrix_vector, int matrix_or
     if (matrix_height != matrix_order) return {};
 
     const size_t count = (size_t)matrix_order * (size_t)matrix_order;
-    std::vector<float> result;
-    try {
-        result.resize(count);
-    } catch (...) {
-        return {};
-    }
+    // The argument arrives BY VALUE (LIB/mat_inv_32.h:4): this copy is ours, so the inverse is written over it and the vector
+    // is moved out -- no second N x N allocation (value-initialising a fresh 1 GiB vector at N = 16384 costs more than
+    // the PCIe transfer).  The reference allocates a separate result (LIB:379); the caller cannot tell the difference.
+    float *const io = matrix_vector.data();
     int flags = 0;
     const char *verbose = std::getenv("MATINV_VERBOSE");
     if (verbose && verbose[0] && verbose[0] != '0') flags |= MATINV_FLAG_VERBOSE;
@@ -42,9 +40,12 @@ std::vector<float> matrix_inv_32(std::vector<float> matrix_vector, int matrix_or
     const char *ng = std::getenv("MATINV_NGPU");
     const int ngpu = ng ? std::atoi(ng) : 1;
     const int rc = (ngpu > 1 && matrix_order >= 4096 && !(flags & MATINV_FLAG_TF32X3))
-                       ? matinv_invert_sharded_f32(matrix_vector.data(), matrix_order, result.data(), nullptr, ngpu, 0, flags & MATINV_FLAG_VERBOSE)
-                       : matinv_invert_f32(matrix_vector.data(), matrix_order, result.data(), nullptr, flags);
-    if (rc == MATINV_OK) return result;
+                       ? matinv_invert_sharded_f32(io, matrix_order, io, nullptr, ngpu, 0, flags & MATINV_FLAG_VERBOSE)
+                       : matinv_invert_f32(io, matrix_order, io, nullptr, flags);
+    if (rc == MATINV_OK) {
+        matrix_vector.resize(count);   // drops the ignored tail of an N*N + k input (LIB:212-215)
+        return matrix_vector;
+    }
     if (rc < 0) std::cerr << "ERRORE N\xC2\xB0: " << rc << " (" << matinv_last_error() << ")" << std::endl;  // LIB:392
     return {};
 }

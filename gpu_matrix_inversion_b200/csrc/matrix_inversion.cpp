@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <limits>
+#include <utility>
 
 #include "../../include/mat_inv_32.h"
 #include "../../include/matinv_shim.h"
@@ -27,14 +28,12 @@ std::vector<double> invert_f64(std::vector<double> &matrix_vector, int matrix_or
     if (matrix_order <= 0) return {};
     const int matrix_height = int(matrix_vector.size() / (size_t)matrix_order);
     if (matrix_height != matrix_order) return {};
-    std::vector<double> result;
-    try {
-        result.resize((size_t)matrix_order * (size_t)matrix_order);
-    } catch (...) {
-        return {};
+    // the caller's by-value copy is ours: the inverse is written over it and moved out (see mat_inv_32.cpp)
+    const int rc = matinv_invert_f64(matrix_vector.data(), matrix_order, matrix_vector.data(), nullptr, flags | env_flags());
+    if (rc == MATINV_OK) {
+        matrix_vector.resize((size_t)matrix_order * (size_t)matrix_order);
+        return std::move(matrix_vector);
     }
-    const int rc = matinv_invert_f64(matrix_vector.data(), matrix_order, result.data(), nullptr, flags | env_flags());
-    if (rc == MATINV_OK) return result;
     if (rc < 0) std::cerr << "ERRORE N\xC2\xB0: " << rc << " (" << matinv_last_error() << ")" << std::endl;
     return {};
 }

@@ -463,13 +463,23 @@ import gpu_matrix_inversion_b200 as m
 from oracle.gj_oracle import SEED_UNIFORM
 out = []
 for n in (int(a) for a in sys.argv[1:]):
-    A = m.generate_dev(n, SEED_UNIFORM + n, "uniform").cpu().numpy()
-    X, piv = m.invert(A, want_piv=True)
+    Ad = m.generate_dev(n, SEED_UNIFORM + n, "uniform")
+    # pinned buffers: the upload is pipelined in column windows (unless MATINV_H2D_PIPELINE=0)
+    Ah = torch.empty((n, n), dtype=torch.float32, pin_memory=True); Xh = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
+    Ah.copy_(Ad); torch.cuda.synchronize()
+    piv = np.empty(n, dtype=np.int32)
+    assert m.lib.matinv_invert_f32(Ah.data_ptr(), n, Xh.data_ptr(), piv.ctypes.data, 0) == 0
+    out.append(hashlib.sha256(piv.tobytes() + Xh.numpy().tobytes()).hexdigest())
+    Ah[:, n - 3] = 0.0                          # singular in the LAST column window
+    assert m.lib.matinv_invert_f32(Ah.data_ptr(), n, Xh.data_ptr(), None, 0) == 1
+    # pageable buffers (numpy / std::vector): parallel staging through pinned memory (unless MATINV_STAGING=0), in place
+    A = Ad.cpu().numpy()
+    X, piv2 = m.invert(A, want_piv=True)
     assert X is not None
-    out.append(hashlib.sha256(piv.tobytes() + X.tobytes()).hexdigest())
-    S = A.copy(); S[:, n - 3] = 0.0            # singular in the LAST column window
-    assert m.invert(S) is None
-    ph = m.last_phases()
+    out.append(hashlib.sha256(piv2.tobytes() + X.tobytes()).hexdigest())
+    io = A.copy()
+    assert m.lib.matinv_invert_f32(io.ctypes.data, n, io.ctypes.data, None, 0) == 0      # A_host == X_host, as matrix_inv_32 calls it
+    out.append(hashlib.sha256(piv2.tobytes() + io.tobytes()).hexdigest())
 print("PIPE", *out)
 """
 
@@ -477,8 +487,9 @@ print("PIPE", *out)
 def test_pipelined_upload_bit_identical(m):
     """The host entry uploads A in column windows and starts factoring when the first one has landed; later windows join at
     a later panel and replay the panels they missed (csrc/matinv_shim.cu:schedule_lookahead_pipelined).  Same bits as the
-    plain upload (MATINV_H2D_PIPELINE=0) and, at N=8320, as the oracle's committed hash -- for the default 4 windows, for 3 and 2, and
-    for a ragged order (9001) whose last window carries the padding."""
+    plain upload (MATINV_H2D_PIPELINE=0) and, at N=8320, as the oracle's committed hash -- for the default windows, for 3 and 2, and
+    for a ragged order (9001) whose last window carries the padding.  Pageable buffers (numpy / std::vector) take the parallel
+    pinned staging instead (MATINV_STAGING), also with A_host == X_host as `matrix_inv_32` calls the entry: same bits."""
     import json
     import os
     import subprocess
@@ -488,7 +499,7 @@ def test_pipelined_upload_bit_identical(m):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     gold = json.loads((Path(__file__).parent / "golden" / "large_sha256.json").read_text())
     seen = []
-    for extra in ({"MATINV_H2D_PIPELINE": "0"}, {}, {"MATINV_H2D_WINDOWS": "3"}, {"MATINV_H2D_WINDOWS": "2"}):
+    for extra in ({"MATINV_H2D_PIPELINE": "0", "MATINV_STAGING": "0"}, {}, {"MATINV_H2D_WINDOWS": "3"}, {"MATINV_H2D_WINDOWS": "2"}):
         env = {k: v for k, v in os.environ.items() if not k.startswith("MATINV_")}
         env.update(extra)
         env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
@@ -496,4 +507,5 @@ def test_pipelined_upload_bit_identical(m):
         assert r.returncode == 0, (extra, r.stderr[-3000:])
         seen.append([l for l in r.stdout.splitlines() if l.startswith("PIPE")][-1].split()[1:])
     assert all(h == seen[0] for h in seen[1:]), seen
-    assert seen[0][0] == gold["8320"]["sha256_piv_X"]
+    assert seen[0][0] == seen[0][1] == seen[0][2] == gold["8320"]["sha256_piv_X"]     # pinned == pageable == in place == oracle
+    assert seen[0][3] == seen[0][4] == seen[0][5]
