@@ -103,15 +103,20 @@ __global__ void pack_columns_kernel(const float *__restrict__ Wl, long long ld, 
         out[e] = Wl[i * ld + cols[k]];
     }
 }
-// Out[i * ld + cols[k]] = recvbuf[i * cnt + k]
+// Out[i * ld + cols[k]] = recvbuf[i * cnt + k]; *nonfinite is raised when an entry of the inverse is not finite (the scan the
+// single-GPU extraction does, SURVEY A.2 -- on the device: scanning N^2 floats on one host thread costs a second at N = 32768)
 __global__ void unpack_columns_kernel(float *__restrict__ Out, long long ld, int n, const int *__restrict__ cols, int cnt,
-                                      const float *__restrict__ in) {
+                                      const float *__restrict__ in, int *__restrict__ nonfinite) {
     const long long total = (long long)n * cnt;
+    bool bad = false;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e / cnt;
         const int k = (int)(e - i * cnt);
-        Out[i * ld + cols[k]] = in[e];
+        const float v = in[e];
+        bad |= !isfinite(v);
+        Out[i * ld + cols[k]] = v;
     }
+    if (bad) *nonfinite = 1;
 }
 
 // ---------------------------------------------------------------------------------------------- helpers
@@ -233,6 +238,30 @@ char *pin_slots(int dev, size_t slot_bytes) {
     return ps.p;
 }
 
+// rows [0, n) of a strided 2-D host copy (rb bytes per row), split over `helpers` threads: one thread moves 512-byte row
+// segments at under 2 GB/s (TLB / cache misses on every row), and with few GPUs one thread per rank is far too little
+void copy_rows_parallel(char *dst, size_t dst_pitch, const char *src, size_t src_pitch, size_t rb, int n, int helpers) {
+    auto body = [&](int h) {
+        const int lo = (int)((long long)n * h / helpers), hi = (int)((long long)n * (h + 1) / helpers);
+        for (int i = lo; i < hi; i++) memcpy(dst + (size_t)i * dst_pitch, src + (size_t)i * src_pitch, rb);
+    };
+    if (helpers <= 1) { body(0); return; }
+    std::vector<std::thread> th;
+    for (int h = 1; h < helpers; h++) th.emplace_back(body, h);
+    body(0);
+    for (auto &t : th) t.join();
+}
+int transfer_helpers(int ngpu) {
+    static int total = -1;
+    if (total < 0) {
+        const char *e = getenv("MATINV_MULTI_COPY_THREADS");
+        total = e ? atoi(e) : 16;
+        if (total < 1) total = 1;
+    }
+    const int k = total / (ngpu > 0 ? ngpu : 1);
+    return k < 1 ? 1 : k;
+}
+
 struct RankState {
     matinv_shard_t *sh = nullptr;
     void *msg[2] = {nullptr, nullptr};
@@ -299,6 +328,7 @@ struct Shared {
     std::vector<int> piv;          // rank 0's copy after the factorisation
     std::vector<int> colsrc;
     int info = 0;
+    volatile int nonfinite = 0;    // an entry of the assembled inverse is not finite
     bool exchange = true;          // apply the deferred column permutation across ranks (false: factorisation only)
     double compute_ms = 0.0;
     Shared(int g) : bar(g) {}
@@ -333,7 +363,8 @@ void rank_factor(int g, Shared &sh, RankState &S) {
         long long lcols = 0, lld = 0;
         matinv_shard_local(S.sh, &lcols, &lld);
         const size_t cnt = (size_t)std::max<long long>(lcols, 1);
-        RCK(cudaMalloc(&S.cols_dev, 2 * cnt * sizeof(int)));
+        RCK(cudaMalloc(&S.cols_dev, (2 * cnt + 1) * sizeof(int)));
+        RCK(cudaMemset(S.cols_dev + 2 * cnt, 0, sizeof(int)));   // the non-finite flag lives behind the two column lists
         if (sh.exchange) {
             RCK(cudaMalloc(&S.sendbuf, cnt * n * sizeof(float)));
             RCK(cudaMalloc(&S.recvbuf, cnt * n * sizeof(float)));
@@ -354,7 +385,7 @@ void rank_factor(int g, Shared &sh, RankState &S) {
             if (it >= 2) RCK(cudaEventSynchronize(S.ev_slot[it & 1]));
             const size_t rb = (size_t)ncols * sizeof(float);
             const float *src = sh.A_host + (size_t)J * MATINV_NB;
-            for (int i = 0; i < n; i++) memcpy(slot + (size_t)i * rb, src + (size_t)i * n, rb);
+            copy_rows_parallel(slot, rb, (const char *)src, (size_t)n * sizeof(float), rb, n, transfer_helpers(G));
             RCK(cudaMemcpy2DAsync(Wl + (size_t)(J / G) * MATINV_NB, (size_t)lld * sizeof(float), slot, rb, rb, (size_t)n, cudaMemcpyHostToDevice, S.main));
             RCK(cudaEventRecord(S.ev_slot[it & 1], S.main));
         }
@@ -494,7 +525,8 @@ void rank_exchange(int g, Shared &sh, RankState &S) {
         if (!cnt) continue;
         const long long total = (long long)n * cnt;
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-        unpack_columns_kernel<<<blocks, 256, 0, S.main>>>(S.Out, lcols, n, S.cols_dev + tot_send + roff[p], cnt, S.recvbuf + roff[p] * n);
+        unpack_columns_kernel<<<blocks, 256, 0, S.main>>>(S.Out, lcols, n, S.cols_dev + tot_send + roff[p], cnt, S.recvbuf + roff[p] * n,
+                                                          S.cols_dev + 2 * (size_t)std::max<long long>(lcols, 1));
     }
     RCK(cudaGetLastError());
     RCK(cudaEventRecord(S.ev_t1, S.main));      // end of the device-resident window (factorisation + column exchange)
@@ -521,10 +553,13 @@ void rank_exchange(int g, Shared &sh, RankState &S) {
             const size_t rb = (size_t)std::min(MATINV_NB, n - J * MATINV_NB) * sizeof(float);
             const char *slot = pin + (size_t)(it & 1) * slot_bytes;
             float *dst = sh.X_host + (size_t)J * MATINV_NB;
-            for (int i = 0; i < n; i++) memcpy(dst + (size_t)i * n, slot + (size_t)i * rb, rb);
+            copy_rows_parallel((char *)dst, (size_t)n * sizeof(float), slot, rb, rb, n, transfer_helpers(G));
         }
     }
+    int flag = 0;
+    RCK(cudaMemcpyAsync(&flag, S.cols_dev + 2 * (size_t)std::max<long long>(lcols, 1), sizeof(int), cudaMemcpyDeviceToHost, S.main));
     RCK(cudaStreamSynchronize(S.main));
+    if (flag) sh.nonfinite = 1;   // (ranks only ever write 1)
 }
 
 thread_local double g_last_sharded_ms = -1.0;
@@ -617,6 +652,7 @@ int run_sharded(const float *A_host, int n, float *X_host, int *piv_host, int ng
         if (sh.info > 0) return shim_fail(MATINV_SINGULAR, "singular: zero or non-finite pivot at column %d", sh.info - 1);
         return shim_fail(MATINV_SINGULAR, "singular: non-finite entry in the inverse");
     }
+    if (sh.nonfinite && !(flags & MATINV_FLAG_NOCHECK)) return shim_fail(MATINV_SINGULAR, "singular: non-finite entry in the inverse");
     return MATINV_OK;
 }
 
@@ -648,15 +684,7 @@ int matinv_invert_sharded_f32(const float *A_host, int n, float *X_host, int *pi
     if (nb != 0 && nb != MATINV_NB) return shim_fail(MATINV_E_UNSUPPORTED, "column blocks are %d wide (nb = 0 selects the default)", MATINV_NB);
     if (flags & (MATINV_FLAG_TF32X3 | MATINV_FLAG_UNBLOCKED))
         return shim_fail(MATINV_E_UNSUPPORTED, "the column-sharded path runs the bit-exact blocked FP32 schedule only");
-    const int rc = run_sharded(A_host, n, X_host, piv_host, ngpu, flags, 0ull, 0, true);
-    // the non-finite scan of the single-GPU extraction (SURVEY A.2 superset rule) on the assembled result
-    if (rc == MATINV_OK && !(flags & MATINV_FLAG_NOCHECK)) {
-        const size_t cnt = (size_t)n * n;
-        bool bad = false;
-        for (size_t k = 0; k < cnt && !bad; k++) bad = !std::isfinite(X_host[k]);
-        if (bad) return shim_fail(MATINV_SINGULAR, "singular: non-finite entry in the inverse");
-    }
-    return rc;
+    return run_sharded(A_host, n, X_host, piv_host, ngpu, flags, 0ull, 0, true);   // (non-finite scan: unpack kernel)
 }
 
 int matinv_sharded_synthetic_f32(int n, unsigned long long seed, int kind, int ngpu, int *piv_host, double *compute_ms) {

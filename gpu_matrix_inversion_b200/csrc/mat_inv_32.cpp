@@ -35,11 +35,15 @@ std::vector<float> matrix_inv_32(std::vector<float> matrix_vector, int matrix_or
     // reference's FMA chain) -- the signature clibgen binds cannot carry a flag, so the switch is an environment variable
     const char *tc = std::getenv("MATINV_TF32X3");
     if (tc && tc[0] && tc[0] != '0') flags |= MATINV_FLAG_TF32X3;
-    // opt-in: MATINV_NGPU = k > 1 column-shards one inversion over k GPUs (bit-identical result; worth it from a few
-    // thousand rows up -- below that one GPU is faster and the single-device path is used)
+    // opt-in: MATINV_NGPU = k > 1 column-shards one inversion over k GPUs (bit-identical result).  From host memory the
+    // transfers dominate below N ~ 32768 (measured with std::vector buffers: N=32768 1.54 s on one GPU, 1.4-1.9 s on 2-8; the
+    // device-resident schedule itself scales 7.9 x on 8 GPUs at N=65536), so smaller orders stay on the single-device path
+    // unless MATINV_NGPU_MIN_ORDER says otherwise
     const char *ng = std::getenv("MATINV_NGPU");
     const int ngpu = ng ? std::atoi(ng) : 1;
-    const int rc = (ngpu > 1 && matrix_order >= 4096 && !(flags & MATINV_FLAG_TF32X3))
+    const char *mo = std::getenv("MATINV_NGPU_MIN_ORDER");
+    const int min_order = mo ? std::atoi(mo) : 32768;
+    const int rc = (ngpu > 1 && matrix_order >= min_order && !(flags & MATINV_FLAG_TF32X3))
                        ? matinv_invert_sharded_f32(io, matrix_order, io, nullptr, ngpu, 0, flags & MATINV_FLAG_VERBOSE)
                        : matinv_invert_f32(io, matrix_order, io, nullptr, flags);
     if (rc == MATINV_OK) {

@@ -116,6 +116,7 @@ int main(int argc, char **argv) {
         env = {k: v for k, v in os.environ.items() if k != "MATINV_NGPU"}
         if ng is not None:
             env["MATINV_NGPU"] = str(ng)
+            env["MATINV_NGPU_MIN_ORDER"] = "4096"      # the default threshold (32768) would keep this order on one GPU
         p = subprocess.run([str(exe)], env=env, capture_output=True, text=True, timeout=600)
         lines = [l for l in p.stdout.splitlines() if l.startswith("HASH")]     # (NCCL may print its version banner first)
         assert p.returncode == 0 and len(lines) == 1, (ng, p.stdout, p.stderr[-2000:])
