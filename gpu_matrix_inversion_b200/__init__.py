@@ -42,7 +42,7 @@ EXPORTS = [
     "matinv_residual_f32_dev", "matinv_last_timing", "matinv_ffma_peak_tflops", "matinv_profile_enable",
     "matinv_profile_read", "matinv_debug_trace", "matinv_invert_f64", "matinv_invert_f64_dev", "matinv_residual_f64_dev",
     "matinv_host_defect_f64", "matinv_tf32x3_status", "matinv_debug_trailing_update", "matinv_probe_residual_f32_dev", "matinv_tf32x3_gate_dev", "matinv_invert_sharded_f32", "matinv_sharded_synthetic_f32",
-    "matinv_invert_batched_f32_ngpu", "matinv_nccl_version", "matinv_last_phases",
+    "matinv_invert_batched_f32_ngpu", "matinv_nccl_version", "matinv_last_phases", "matinv_debug_pipeline_plan",
 ]
 
 
@@ -77,6 +77,8 @@ def _load() -> ctypes.CDLL:
     L.matinv_last_timing.argtypes = [dp, dp]
     L.matinv_last_phases.argtypes = [dp]
     L.matinv_last_phases.restype = i
+    L.matinv_debug_pipeline_plan.argtypes = [i, ip, ip, ip, ip, ip]
+    L.matinv_debug_pipeline_plan.restype = i
     L.matinv_ffma_peak_tflops.argtypes = [dp, vp]
     L.matinv_profile_enable.argtypes = [i]
     L.matinv_profile_enable.restype = None

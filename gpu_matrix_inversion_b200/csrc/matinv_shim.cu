@@ -1321,6 +1321,17 @@ int matinv_host_defect_f64(const double *A_host, const double *B_host, int n, do
     return MATINV_OK;
 }
 
+int matinv_debug_pipeline_plan(int n, int *nwin, int *c0_8, int *ncols_8, int *act_8, int *ring_slots) {
+    if (n <= 0 || !nwin || !c0_8 || !ncols_8 || !act_8) return MATINV_E_INVALID;
+    PipePlan P;
+    const int npad = ((n + MATINV_NB - 1) / MATINV_NB) * MATINV_NB;
+    if (!plan_pipeline(n, npad, 0, P)) { *nwin = 0; return 0; }
+    *nwin = P.nwin;
+    for (int w = 0; w < P.nwin; w++) { c0_8[w] = P.c0[w]; ncols_8[w] = P.ncols[w]; act_8[w] = P.act[w]; }
+    if (ring_slots) *ring_slots = P.ringfix + 2;
+    return 1;
+}
+
 int matinv_last_phases(double *out5) {
     if (!out5 || g_phase[4] < 0) return 1;
     for (int i = 0; i < 5; i++) out5[i] = g_phase[i];

@@ -161,6 +161,13 @@ int matinv_last_timing(double *total_s, double *compute_s);
  * ("matinv_invert_f32", "H2D", ...) for Nsight Systems.  Returns 0 if available (not for MATINV_FLAG_TF32X3 calls). */
 int matinv_last_phases(double *out5);
 
+/* Host logic of the pipelined upload of matinv_invert_f32 (pinned buffers, n >= 8192), exposed so that its
+ * invariants can be tested without a GPU: the column windows (start column c0, width ncols, both multiples of 128, tiling
+ * [0, npad)), the panel at which each window joins (act; window w must be active before its first block becomes the
+ * look-ahead block: act[w] <= c0[w] / 128 - 1) and the number of message slots kept.  Arrays of 8.  Returns 1 if this order is
+ * pipelined, 0 if not (then *nwin = 0), < 0 on a bad argument.  Makes no CUDA call. */
+int matinv_debug_pipeline_plan(int n, int *nwin, int *c0_8, int *ncols_8, int *act_8, int *ring_slots);
+
 /* Profiling hooks for bench.py.  With profiling enabled the shim brackets every trailing-update
  * (GEMM) launch with CUDA events on the launching stream.  matinv_profile_read returns, for the
  * calls made since the last matinv_profile_enable: summed GEMM time (ms), number of GEMM launches,

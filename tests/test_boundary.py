@@ -71,6 +71,40 @@ def test_multi_gpu_entries_argument_checks_without_device():
         assert m.last_phases() is None
 
 
+def test_pipelined_upload_plan_invariants():
+    """Host logic of the pipelined upload (csrc/matinv_shim.cu:plan_pipeline), no GPU needed: for every order the column
+    windows tile [0, npad) in multiples of 128, join in order, and every window is active before its first block becomes the
+    look-ahead block of the panel chain -- the invariant schedule_lookahead_pipelined relies on."""
+    import ctypes
+
+    import gpu_matrix_inversion_b200 as m
+
+    def plan(n, env_windows=None):
+        nwin = ctypes.c_int(0)
+        ring = ctypes.c_int(0)
+        c0 = (ctypes.c_int * 8)()
+        nc = (ctypes.c_int * 8)()
+        act = (ctypes.c_int * 8)()
+        rc = m.lib.matinv_debug_pipeline_plan(n, ctypes.byref(nwin), c0, nc, act, ctypes.byref(ring))
+        return rc, nwin.value, list(c0)[:nwin.value], list(nc)[:nwin.value], list(act)[:nwin.value], ring.value
+
+    assert m.lib.matinv_debug_pipeline_plan(0, None, None, None, None, None) == m.E_INVALID
+    assert plan(4096)[0] == 0 and plan(8191)[0] == 0            # small orders are not pipelined
+    assert plan(70000)[0] == 0                                  # beyond the cluster panel path (n > 65536)
+    orders = list(range(8192, 20000, 257)) + [8192, 8320, 9001, 16384, 16385, 32768, 32896, 40000, 65536]
+    for n in orders:
+        rc, nwin, c0, nc, act, ring = plan(n)
+        assert rc == 1 and 2 <= nwin <= 6, n
+        npad = (n + 127) // 128 * 128
+        assert c0[0] == 0 and sum(nc) == npad, (n, c0, nc)
+        assert all(c % 128 == 0 and w % 128 == 0 and w >= 8 * 128 for c, w in zip(c0, nc)), (n, c0, nc)
+        assert all(c0[w] == c0[w - 1] + nc[w - 1] for w in range(1, nwin)), (n, c0, nc)
+        assert act[0] == 0 and all(act[w] >= max(1, act[w - 1]) for w in range(1, nwin)), (n, act)
+        assert all(act[w] <= c0[w] // 128 - 1 for w in range(1, nwin)), (n, act, c0)
+        assert ring == max(act) + 2
+        assert c0[-1] < n                                       # the last window holds real columns, not only padding
+
+
 def test_cpp_surface_links_and_follows_conventions(tmp_path):
     """Compile a caller against include/mat_inv_32.h exactly like a user of the reference header."""
     src = tmp_path / "caller.cpp"
