@@ -110,7 +110,10 @@ def _worker(rank, world, port, n, kind, q):
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     A = {"uniform": o.uniform, "hollow": lambda k: o.hollow(k)[0], "singular": lambda k: np.where(np.arange(k)[:, None] == 7, 0, o.uniform(k)).astype(f32)}[kind](n)
-    inv = ShardedInverter(NumpyShardBackend(n, rank, world, A), dist if world > 1 else None)
+    # the per-block broadcasts may run on their own process group (bench.py: an NCCL group limited to a few CTAs); here a
+    # second gloo group over the same ranks, so that the group plumbing of ShardedInverter is exercised on CPU
+    bgroup = dist.new_group(ranks=list(range(world))) if world > 1 and kind != "hollow" else None
+    inv = ShardedInverter(NumpyShardBackend(n, rank, world, A), dist if world > 1 else None, bcast_group=bgroup)
     info, piv, blocks = inv.invert()
     out = {J: t.numpy().copy() for J, t in blocks.items()} if blocks is not None else None
     q.put((rank, info, piv, out))
