@@ -28,6 +28,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cmath>
 #include <mutex>
@@ -329,6 +331,7 @@ struct Shared {
     std::vector<int> colsrc;
     int info = 0;
     volatile int nonfinite = 0;    // an entry of the assembled inverse is not finite
+    std::atomic<int> abort{0};     // a rank failed inside the block loop: the others stop issuing collectives
     bool exchange = true;          // apply the deferred column permutation across ranks (false: factorisation only)
     double compute_ms = 0.0;
     Shared(int g) : bar(g) {}
@@ -422,6 +425,11 @@ void rank_schedule(int g, Shared &sh, RankState &S) {
     if (owner_of(0, G) == g) RMK(matinv_shard_factor(S.sh, 0, S.msg[0], S.main));
     if (G > 1) RNK(g_nccl.Broadcast(S.msg[0], S.msg[0], mbytes, ncclChar, owner_of(0, G), comm, S.main));
     for (int J = 0; J < nblk; J++) {
+        if (sh.abort.load(std::memory_order_relaxed)) {
+            snprintf(S.err, sizeof(S.err), "aborted: another rank failed");
+            S.rc = MATINV_E_CUDA;
+            return;
+        }
         void *msg = S.msg[J & 1];
         const int nxt = J + 1;
         if (nxt >= nblk) {
@@ -599,7 +607,23 @@ int run_sharded(const float *A_host, int n, float *X_host, int *piv_host, int ng
         sh.bar.wait();
         const bool ok1 = !any_failed();          // every rank sees the same verdict: all ranks wrote rc before the barrier
         if (ok1) rank_schedule(g, sh, S);
+        if (ok1 && S.rc < 0 && !sh.abort.exchange(1) && ngpu > 1) {
+            // This rank failed in the middle of the block loop: the collectives the others have already posted would wait
+            // for it forever.  Aborting the communicators makes them return (the call fails as a whole and the
+            // communicators are rebuilt by the next one).  The other ranks poll `abort` once per block step (~0.1-1 ms of
+            // enqueue work): give them time to stop issuing collectives on the handles that are about to go away.
+            std::this_thread::sleep_for(std::chrono::milliseconds(100));
+            for (ncclComm_t c : g_comms.bcast) if (c) g_nccl.CommAbort(c);
+            for (ncclComm_t c : g_comms.comm) if (c) g_nccl.CommAbort(c);
+            g_comms.bcast.clear();
+            g_comms.comm.clear();
+            g_comms.ngpu = 0;
+        }
         if (ok1 && S.rc == 0) rank_status(g, sh, S, pivs[g], infos[g]);
+        if (ok1 && S.rc == 0 && sh.abort.load()) {
+            snprintf(S.err, sizeof(S.err), "aborted: another rank failed");
+            S.rc = MATINV_E_CUDA;
+        }
         sh.bar.wait();
         const bool ok2 = ok1 && !any_failed();
         if (ok2 && g == 0) {
@@ -639,7 +663,7 @@ int run_sharded(const float *A_host, int n, float *X_host, int *piv_host, int ng
     }
     cudaSetDevice(cur);
     if (rc < 0) {
-        if (ngpu > 1) {   // a failed rank may have left collectives half-issued: the communicators are not reusable
+        if (ngpu > 1 && g_comms.ngpu) {   // a failed rank may have left collectives half-issued: the communicators are not reusable
             for (ncclComm_t c : g_comms.bcast) if (c) g_nccl.CommAbort(c);
             for (ncclComm_t c : g_comms.comm) if (c) g_nccl.CommAbort(c);
             g_comms.bcast.clear();
